@@ -1,0 +1,134 @@
+"""Thin object wrapper over one ``ab200_solver`` handle (one GPU, one row block)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class DeviceSolver:
+    """Owns the device state of one Krylov-Schur solve: basis V, CSR block of A, H copy.
+
+    Replaces the allocations at krylov_schur.py:42-43 and the three n-length call
+    sites decomposition.py:58,60 and krylov_schur.py:78-81.
+    """
+
+    def __init__(self, n, max_dim, *, device=0, row0=0, nrows_local=None):
+        self.lib = _lib.load()
+        self.n_global = int(n)
+        self.n = int(n if nrows_local is None else nrows_local)
+        self.row0 = int(row0)
+        self.max_dim = int(max_dim)
+        self._h = C.c_void_p()
+        _lib.check(self.lib.ab200_create(C.byref(self._h), int(device), self.n_global, self.row0,
+                                         self.n, self.max_dim))
+        # column-major staging area for the H columns an expansion returns
+        self._hbuf = np.zeros((self.max_dim + 1, self.max_dim), np.complex128, order="F")
+
+    # -- lifetime ---------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.ab200_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- operator ---------------------------------------------------------------
+    def set_csr(self, indptr, indices, data, *, algo=_lib.SPMV_AUTO):
+        """Upload a CSR row block exactly as scipy stores it (no re-ordering)."""
+        indptr = np.ascontiguousarray(indptr)
+        if indptr.dtype not in (np.int32, np.int64):
+            indptr = indptr.astype(np.int64)
+        indices = np.ascontiguousarray(indices, dtype=np.int32)
+        if np.iscomplexobj(data):
+            data = np.ascontiguousarray(data, dtype=np.complex128)
+            kind = _lib.C128
+        else:
+            data = np.ascontiguousarray(data, dtype=np.float64)
+            kind = _lib.F64
+        assert indptr.shape == (self.n + 1,), "indptr must have nrows_local + 1 entries"
+        assert indices.shape == data.shape, "indices and data differ in length"
+        _lib.check(self.lib.ab200_set_csr(self._h, _ptr(indptr), indptr.dtype.itemsize * 8,
+                                          _ptr(indices), _ptr(data), kind, int(data.shape[0]),
+                                          int(algo)))
+        self.nnz = int(data.shape[0])
+        self.value_kind = kind
+
+    # -- basis ------------------------------------------------------------------
+    def set_columns(self, col0, cols):
+        cols = np.asarray(cols, dtype=np.complex128)
+        if cols.ndim == 1:
+            cols = cols.reshape(-1, 1)
+        cols = np.asfortranarray(cols)
+        assert cols.shape[0] == self.n
+        _lib.check(self.lib.ab200_set_columns(self._h, int(col0), int(cols.shape[1]), _ptr(cols),
+                                              int(cols.shape[0])))
+
+    def get_columns(self, col0, ncols, out=None):
+        if out is None:
+            out = np.empty((self.n, ncols), np.complex128, order="F")
+        assert out.flags.f_contiguous and out.shape == (self.n, ncols)
+        _lib.check(self.lib.ab200_get_columns(self._h, int(col0), int(ncols), _ptr(out), self.n))
+        return out
+
+    # -- hot path ---------------------------------------------------------------
+    def expand(self, start_dim, end_dim, tol, *, eta=np.sqrt(0.5), ortho=_lib.ORTHO_CGS2):
+        """decomposition.py:56-66 on the device.  Returns (H columns view, n_iter, breakdown).
+
+        The returned array is column-major (max_dim+1) x max_dim; only columns
+        [start_dim, n_iter) are meaningful (rows 0..j+1 of column j).
+        """
+        n_iter, brk = C.c_int(0), C.c_int(0)
+        _lib.check(self.lib.ab200_expand(self._h, int(start_dim), int(end_dim), float(tol),
+                                         float(eta), int(ortho), _ptr(self._hbuf),
+                                         C.byref(n_iter), C.byref(brk)))
+        return self._hbuf, n_iter.value, bool(brk.value)
+
+    def restart(self, Q, m, p):
+        """krylov_schur.py:78,81:  V[:, :p] = V[:, :m] Q[:, :p];  V[:, p] = V[:, m]."""
+        q = np.asfortranarray(Q[:m, :p], dtype=np.complex128)
+        _lib.check(self.lib.ab200_restart(self._h, _ptr(q), int(m), int(m), int(p)))
+
+    def spmv(self, x):
+        x = np.ascontiguousarray(x, dtype=np.complex128)
+        assert x.shape == (self.n_global,)
+        y = np.empty(self.n, np.complex128)
+        _lib.check(self.lib.ab200_spmv(self._h, _ptr(x), _ptr(y)))
+        return y
+
+    def ortho(self, ncols, w, h, tol, eta, kind):
+        """In place on contiguous complex128 ``w`` (n) and ``h`` (ncols)."""
+        beta, brk = C.c_double(0.0), C.c_int(0)
+        _lib.check(self.lib.ab200_ortho(self._h, int(ncols), _ptr(w), _ptr(h), float(tol),
+                                        float(eta), int(kind), C.byref(beta), C.byref(brk)))
+        return beta.value, bool(brk.value)
+
+    # -- measurement ------------------------------------------------------------
+    def set_timing(self, on=True):
+        _lib.check(self.lib.ab200_set_timing(self._h, int(bool(on))))
+
+    def reset_stats(self):
+        _lib.check(self.lib.ab200_reset_stats(self._h))
+
+    def stats(self):
+        st = _lib.Stats()
+        _lib.check(self.lib.ab200_get_stats(self._h, C.byref(st)))
+        return st.as_dict()
+
+    def synchronize(self):
+        _lib.check(self.lib.ab200_synchronize(self._h))
+
+    def set_option(self, key, value):
+        _lib.check(self.lib.ab200_set_option(self._h, key.encode(), int(value)))

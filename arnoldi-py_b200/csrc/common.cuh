@@ -1,0 +1,109 @@
+// common.cuh -- shared device helpers for the sm_100a Krylov-Schur kernels.
+//
+// Everything n-length in this library is complex128 stored as interleaved
+// (re, im) doubles, i.e. one 16-byte element = one 128-bit load.  The Krylov
+// basis is column-major with a padded leading dimension so every column starts
+// on a 128-byte line.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ab200 {
+
+typedef double2 cplx;  // .x = re, .y = im
+
+constexpr int kWarp = 32;
+constexpr int kNumSMsB200 = 148;
+
+// ---------------------------------------------------------------- loads / stores
+// Streaming 128-bit load of read-only data that is touched once per kernel
+// (columns of the Krylov basis): bypass L1 allocation, keep L1 for w / coefficients.
+__device__ __forceinline__ cplx ld_stream(const cplx* p) {
+  cplx r;
+  asm("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  return r;
+}
+// Read-only 128-bit load that may be re-used by neighbouring warps (w, gathered x).
+__device__ __forceinline__ cplx ld_ro(const cplx* p) {
+  cplx r;
+  asm("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  return r;
+}
+// Plain (coherent) 128-bit load for data written earlier in the same kernel family.
+__device__ __forceinline__ cplx ld_plain(const cplx* p) {
+  cplx r;
+  asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ void st_stream(cplx* p, cplx v) {
+  asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y)
+               : "memory");
+}
+
+// ---------------------------------------------------------------- complex arithmetic
+// acc += conj(a) * b        (the inner product <a, b> term, as zgemv trans=2 / vdot)
+__device__ __forceinline__ void cfma_conj(cplx& acc, const cplx a, const cplx b) {
+  acc.x = fma(a.x, b.x, acc.x);
+  acc.x = fma(a.y, b.y, acc.x);
+  acc.y = fma(a.x, b.y, acc.y);
+  acc.y = fma(-a.y, b.x, acc.y);
+}
+// acc += a * b
+__device__ __forceinline__ void cfma(cplx& acc, const cplx a, const cplx b) {
+  acc.x = fma(a.x, b.x, acc.x);
+  acc.x = fma(-a.y, b.y, acc.x);
+  acc.y = fma(a.x, b.y, acc.y);
+  acc.y = fma(a.y, b.x, acc.y);
+}
+// acc -= a * b
+__device__ __forceinline__ void cfms(cplx& acc, const cplx a, const cplx b) {
+  acc.x = fma(-a.x, b.x, acc.x);
+  acc.x = fma(a.y, b.y, acc.x);
+  acc.y = fma(-a.x, b.y, acc.y);
+  acc.y = fma(-a.y, b.x, acc.y);
+}
+__device__ __forceinline__ cplx cadd(const cplx a, const cplx b) {
+  return make_double2(a.x + b.x, a.y + b.y);
+}
+__device__ __forceinline__ cplx cscale(const cplx a, const double s) {
+  return make_double2(a.x * s, a.y * s);
+}
+
+// ---------------------------------------------------------------- reductions
+// Fixed-order butterfly: the result is bit-identical on every lane and from run
+// to run (no atomics on floating point anywhere in this library).
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ cplx warp_sum(cplx v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
+    v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+  }
+  return v;
+}
+
+// "last block done" ticket: returns true in exactly one block, after every other
+// block's global writes that preceded its own ticket are visible.
+__device__ __forceinline__ bool last_block_ticket(unsigned* ticket, unsigned nblocks,
+                                                  int* smem_flag) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    unsigned t = atomicAdd(ticket, 1u);
+    int last = (t == nblocks - 1);
+    if (last) {
+      *ticket = 0;  // ready for the next launch on the same stream
+      __threadfence();
+    }
+    *smem_flag = last;
+  }
+  __syncthreads();
+  return *smem_flag != 0;
+}
+
+}  // namespace ab200

@@ -1,0 +1,75 @@
+// kernels.cuh -- argument blocks and launcher prototypes of the n-length kernels.
+#pragma once
+
+#include "common.cuh"
+#include "state.cuh"
+
+namespace ab200 {
+
+// ---------------------------------------------------------------- orthogonalisation
+struct OrthoArgs {
+  const cplx* U;     // basis, column-major, un-normalised columns (V_i = scale[i] * U_i)
+  cplx* w;           // vector being orthogonalised (column j+1 of the basis, or a scratch vector)
+  int64_t n;         // local rows
+  int64_t ld;        // leading dimension of U in elements
+  int ncols;         // c = number of basis columns to orthogonalise against
+  int j;             // Arnoldi step (H column) -- ncols - 1 inside an expansion
+  int round;         // 1 or 2 (DGKS repeat)
+  int accumulate;    // h += (round 2) instead of h =
+  int finalize;      // write H[j+1, j], scale[j+1], breakdown flag when the step ends
+  int grid_cap;      // capacity (in blocks) of the partial buffers
+  double tol;        // breakdown threshold (absolute, ortho.py:107)
+  double eta;        // DGKS factor (ortho.py:101)
+  double* scale;     // [max_dim + 1]
+  cplx* hcol;        // column j of the device copy of H (max_dim + 1 entries)
+  cplx* coef;        // [max_dim + 1] pass-2 coefficients scale[i] * h_i of the current round
+  cplx* part;        // [(max_dim + 1) * grid_cap] per-block partial dot products
+  double* npart;     // [grid_cap] per-block partial norms
+  unsigned* ticket;  // last-block ticket
+  StepCtl* ctl;
+  int* step_flag;    // nullptr, or where to record that this step ran the second round
+  PeerComm comm;
+};
+
+cudaError_t launch_cgs_pass1(const OrthoArgs& a, int num_sms, cudaStream_t st, int grid_mult);
+cudaError_t launch_cgs_pass2(const OrthoArgs& a, int num_sms, cudaStream_t st, int grid_mult);
+cudaError_t launch_mgs_step(const OrthoArgs& a, int i, int num_sms, cudaStream_t st,
+                            int grid_mult);
+
+// ---------------------------------------------------------------- SpMV
+struct SpmvArgs {
+  const void* indptr;      // [n + 1], 32- or 64-bit, relative to the local block
+  const int32_t* indices;  // [nnz] column ids: < n_local -> local x, else ghost[id - n_local]
+  const void* values;      // [nnz] float64 or complex128
+  const int64_t* rowblk;   // [nblocks + 1] first row of each nnz tile
+  const cplx* x;           // local part of the input vector (un-normalised column)
+  const cplx* ghost;       // halo entries received from peers (nullptr on one GPU)
+  cplx* y;                 // output (local rows)
+  const double* xscale;    // nullptr or pointer to the lazy scale of x
+  int64_t n;               // local rows
+  int64_t n_local_cols;    // column ids below this are local
+  int nblocks;
+  int tile;                // nnz staged per block iteration
+  const StepCtl* ctl;      // nullptr for the stand-alone entry point
+};
+
+cudaError_t launch_spmv(const SpmvArgs& a, int indptr_bits, int value_kind, cudaStream_t st);
+// builds rowblk[b] = first row whose indptr >= b * tile  (b = 0..nblocks), on device
+cudaError_t launch_spmv_plan(const void* indptr, int indptr_bits, int64_t n, int64_t nnz, int tile,
+                             int nblocks, int64_t* rowblk, cudaStream_t st);
+
+// ---------------------------------------------------------------- restart + helpers
+struct RestartArgs {
+  cplx* U;              // basis, updated in place
+  int64_t n, ld;
+  int m, p;
+  const cplx* q;        // device copy of Q[:, :p], row i pre-multiplied by scale[i]; layout [i * p + k]
+  double scale_m;       // scale of column m (applied while it is copied to column p)
+};
+cudaError_t launch_restart(const RestartArgs& a, int num_sms, cudaStream_t st, int variant);
+
+// U[:, col] *= scale[col]; scale[col] = 1   for col in [col0, col0 + ncols)
+cudaError_t launch_materialize(cplx* U, int64_t n, int64_t ld, int col0, int ncols, double* scale,
+                               int num_sms, cudaStream_t st);
+
+}  // namespace ab200

@@ -1,0 +1,503 @@
+// ortho.cu -- fused orthogonalisation kernels (the reference's ortho.py).
+//
+// dgks_gs  (ortho.py:56-107): one round = pass 1  h = V^H w and ||w||^2 in ONE sweep
+//                                          pass 2  w -= V h and ||w||^2 in ONE sweep
+// dgks_mgs (ortho.py:9-53):   one sweep = c+1 kernels, kernel i fuses the axpy of
+//                             column i-1 with the dot product against column i.
+//
+// The basis is stored un-normalised: column i holds U_i with V_i = scale[i] * U_i
+// (scale[i] = 1/beta_i, decomposition.py:65-66), so the reference's `w /= beta`
+// pass over n elements never happens; the scale is folded into the c-length
+// coefficient vectors here.
+//
+// Every reduction is two-stage in a fixed order (lane butterfly -> per-block
+// partial -> last block sums the partials in block order), so results are
+// bit-reproducible run to run.  No floating-point atomics.
+#include "kernels.cuh"
+
+namespace ab200 {
+
+// ------------------------------------------------------------------ finalisers
+// Sum per-block partials of column i in block order: one warp per column.
+__device__ __forceinline__ cplx sum_partials(const cplx* part, int nblocks, int lane) {
+  cplx a = make_double2(0.0, 0.0);
+  for (int b = lane; b < nblocks; b += kWarp) a = cadd(a, part[b]);
+  return warp_sum(a);
+}
+__device__ __forceinline__ double sum_partials(const double* part, int nblocks, int lane) {
+  double a = 0.0;
+  for (int b = lane; b < nblocks; b += kWarp) a += part[b];
+  return warp_sum(a);
+}
+
+// Cross-GPU sum of `count` doubles held in red[] (local result), in rank order.
+// Called by every thread of the last block; returns with red[] = global sums.
+__device__ void peer_allreduce(const PeerComm& pc, double* red, int count, StepCtl* ctl) {
+  if (pc.nranks <= 1) return;
+  __shared__ unsigned long long s_seq;
+  const int tid = threadIdx.x;
+  if (tid == 0) s_seq = *pc.seq + 1ull;
+  __syncthreads();
+  const unsigned long long seq = s_seq;
+  const int par = (int)(seq & 1ull);
+  const size_t slot_off = ((size_t)par * kMaxRanks + pc.rank) * pc.slot_doubles;
+  // 1. push my partial into slot[my rank] of every rank (mine included)
+  for (int r = 0; r < pc.nranks; ++r) {
+    double* dst = pc.slots[r] + slot_off;
+    for (int k = tid; k < count; k += blockDim.x) dst[k] = red[k];
+  }
+  __threadfence_system();
+  __syncthreads();
+  // 2. raise my flag on every rank
+  if (tid < pc.nranks) {
+    volatile unsigned long long* f = pc.flags[tid] + (size_t)par * kMaxRanks + pc.rank;
+    *f = seq;
+  }
+  // 3. wait for every rank's flag in my own flag array
+  if (tid < pc.nranks) {
+    volatile unsigned long long* f = pc.flags[pc.rank] + (size_t)par * kMaxRanks + tid;
+    long long spins = 0;
+    while (*f < seq) {
+      if (++spins > (1ll << 31)) {
+        ctl->comm_error = 1;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  __threadfence_system();
+  // 4. sum in rank order
+  const double* mine = pc.slots[pc.rank] + (size_t)par * kMaxRanks * pc.slot_doubles;
+  for (int k = tid; k < count; k += blockDim.x) {
+    double a = 0.0;
+    for (int r = 0; r < pc.nranks; ++r)
+      a += *((volatile const double*)(mine + (size_t)r * pc.slot_doubles + k));
+    red[k] = a;
+  }
+  __syncthreads();
+  if (tid == 0) *pc.seq = seq;
+}
+
+// After pass 1 (or an MGS dot): g_i -> h_i = s_i g_i, H column, pass-2 coefficients.
+//   red[2*i], red[2*i+1] = g_i ; red[2*ncols] = ||w||^2 (when want_norm)
+__device__ void finish_dots(const OrthoArgs& a, int col0, int ncols, double* red, bool want_norm) {
+  const int tid = threadIdx.x;
+  for (int i = tid; i < ncols; i += blockDim.x) {
+    const double s = a.scale[col0 + i];
+    cplx h = make_double2(red[2 * i] * s, red[2 * i + 1] * s);
+    cplx old = a.hcol[col0 + i];
+    a.hcol[col0 + i] = a.accumulate ? cadd(old, h) : h;
+    a.coef[col0 + i] = cscale(h, s);
+  }
+  if (want_norm && tid == 0) a.ctl->nrm0sq = red[2 * ncols];
+}
+
+// After pass 2 (or the last MGS axpy): beta, DGKS decision, breakdown, H[j+1,j], scale.
+__device__ void finish_norm(const OrthoArgs& a, double nrmsq) {
+  StepCtl* ctl = a.ctl;
+  const double beta = sqrt(nrmsq);
+  ctl->beta = beta;
+  bool again = false;
+  if (a.round == 1) {
+    ctl->rounds_total += 1;
+    // ortho.py:101 `beta < eta * beta_before` (strict)
+    again = beta < a.eta * sqrt(ctl->nrm0sq);
+    ctl->round2 = again ? 1 : 0;
+    if (again) ctl->second_total += 1;
+    if (a.step_flag) *a.step_flag = again ? 1 : 0;
+  } else {
+    ctl->rounds_total += 1;
+    ctl->round2 = 0;
+  }
+  if (!again && a.finalize) {
+    ctl->steps_total += 1;
+    if (beta < a.tol) {  // ortho.py:107, decomposition.py:61-63
+      ctl->stop = 1;
+      ctl->broke_at = a.j;
+      a.scale[a.j + 1] = 1.0;  // the reference leaves w un-normalised
+    } else {
+      a.hcol[a.j + 1] = make_double2(beta, 0.0);  // decomposition.py:65
+      a.scale[a.j + 1] = 1.0 / beta;              // decomposition.py:66, applied lazily
+    }
+  }
+}
+
+// ------------------------------------------------------------------ CGS pass 1
+// Block = W warps.  All warps sweep the SAME rows (so w is read from HBM once and
+// re-used through L1); warp k owns columns [k*CT, k*CT+CT) and keeps their
+// accumulators in registers for the whole kernel.  Lanes run along n, so each
+// load instruction of a warp covers 512 contiguous bytes of one column.
+template <int CT, int R>
+__global__ void __launch_bounds__(512) cgs_pass1_kernel(OrthoArgs a) {
+  StepCtl* ctl = a.ctl;
+  if (ctl->stop) return;
+  if (a.round == 2 && !ctl->round2) return;
+
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int c = a.ncols;
+  const int mycol0 = warp * CT;
+  int mycols = c - mycol0;
+  mycols = mycols < 0 ? 0 : (mycols > CT ? CT : mycols);
+  const int64_t ld = a.ld;
+  const cplx* __restrict__ w = a.w;
+  const cplx* __restrict__ U = a.U + (int64_t)mycol0 * ld;
+
+  cplx acc[CT];
+#pragma unroll
+  for (int k = 0; k < CT; ++k) acc[k] = make_double2(0.0, 0.0);
+  double nacc = 0.0;
+
+  constexpr int ROWS = kWarp * R;
+  const int64_t nchunks = (a.n + ROWS - 1) / ROWS;
+  for (int64_t q = blockIdx.x; q < nchunks; q += gridDim.x) {
+    const int64_t base = q * ROWS + lane;
+    cplx wv[R];
+    cplx v[CT][R];
+    if (q * ROWS + ROWS <= a.n) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) wv[r] = ld_ro(w + base + r * kWarp);
+#pragma unroll
+      for (int k = 0; k < CT; ++k) {
+        if (k < mycols) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) v[k][r] = ld_stream(U + (int64_t)k * ld + base + r * kWarp);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const bool ok = base + r * kWarp < a.n;
+        wv[r] = ok ? ld_ro(w + base + r * kWarp) : make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for (int k = 0; k < CT; ++k) {
+        if (k < mycols) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const bool ok = base + r * kWarp < a.n;
+            v[k][r] = ok ? ld_stream(U + (int64_t)k * ld + base + r * kWarp)
+                         : make_double2(0.0, 0.0);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < CT; ++k) {
+      if (k < mycols) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) cfma_conj(acc[k], v[k][r], wv[r]);
+      }
+    }
+    if (warp == 0) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        nacc = fma(wv[r].x, wv[r].x, nacc);
+        nacc = fma(wv[r].y, wv[r].y, nacc);
+      }
+    }
+  }
+
+  // per-block partials, column-major by block so the final sums are coalesced
+  const int gcap = a.grid_cap;
+#pragma unroll
+  for (int k = 0; k < CT; ++k) {
+    if (k < mycols) {
+      cplx s = warp_sum(acc[k]);
+      if (lane == 0) a.part[(size_t)(mycol0 + k) * gcap + blockIdx.x] = s;
+    }
+  }
+  if (warp == 0) {
+    double s = warp_sum(nacc);
+    if (lane == 0) a.npart[blockIdx.x] = s;
+  }
+
+  __shared__ int s_last;
+  if (!last_block_ticket(a.ticket, gridDim.x, &s_last)) return;
+
+  // ---- last block: reduce across blocks (fixed order), across GPUs, finish
+  extern __shared__ double red[];  // 2*c + 1 doubles
+  const int nwarps = blockDim.x >> 5;
+  for (int i = warp; i < c; i += nwarps) {
+    cplx g = sum_partials(a.part + (size_t)i * gcap, gridDim.x, lane);
+    if (lane == 0) {
+      red[2 * i] = g.x;
+      red[2 * i + 1] = g.y;
+    }
+  }
+  if (warp == 0) {
+    double s = sum_partials(a.npart, gridDim.x, lane);
+    if (lane == 0) red[2 * c] = s;
+  }
+  __syncthreads();
+  peer_allreduce(a.comm, red, 2 * c + 1, ctl);
+  __syncthreads();
+  finish_dots(a, 0, c, red, a.round == 1);
+}
+
+// ------------------------------------------------------------------ CGS pass 2
+// w -= U * coef ; ||w||^2.  Warp = R*32 contiguous rows, all c columns; the
+// coefficients sit in shared memory and are broadcast.
+template <int R, int UC>
+__global__ void __launch_bounds__(256) cgs_pass2_kernel(OrthoArgs a) {
+  StepCtl* ctl = a.ctl;
+  if (ctl->stop) return;
+  if (a.round == 2 && !ctl->round2) return;
+
+  extern __shared__ double smem_d[];
+  cplx* scoef = reinterpret_cast<cplx*>(smem_d);
+  const int c = a.ncols;
+  for (int i = threadIdx.x; i < c; i += blockDim.x) scoef[i] = a.coef[i];
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nwarps = blockDim.x >> 5;
+  const int64_t ld = a.ld;
+  const cplx* __restrict__ U = a.U;
+  cplx* w = a.w;
+  double nacc = 0.0;
+
+  constexpr int ROWS = kWarp * R;
+  const int64_t nchunks = (a.n + ROWS - 1) / ROWS;
+  for (int64_t q = (int64_t)blockIdx.x * nwarps + warp; q < nchunks;
+       q += (int64_t)gridDim.x * nwarps) {
+    const int64_t base = q * ROWS + lane;
+    const bool full = q * ROWS + ROWS <= a.n;
+    cplx acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const bool ok = full || base + r * kWarp < a.n;
+      acc[r] = ok ? ld_plain(w + base + r * kWarp) : make_double2(0.0, 0.0);
+    }
+    int i = 0;
+    if (full) {
+      for (; i + UC <= c; i += UC) {
+        cplx v[UC][R];
+#pragma unroll
+        for (int u = 0; u < UC; ++u)
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+            v[u][r] = ld_stream(U + (int64_t)(i + u) * ld + base + r * kWarp);
+#pragma unroll
+        for (int u = 0; u < UC; ++u) {
+          const cplx cf = scoef[i + u];
+#pragma unroll
+          for (int r = 0; r < R; ++r) cfms(acc[r], v[u][r], cf);
+        }
+      }
+    }
+    for (; i < c; ++i) {
+      cplx v[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const bool ok = full || base + r * kWarp < a.n;
+        v[r] = ok ? ld_stream(U + (int64_t)i * ld + base + r * kWarp) : make_double2(0.0, 0.0);
+      }
+      const cplx cf = scoef[i];
+#pragma unroll
+      for (int r = 0; r < R; ++r) cfms(acc[r], v[r], cf);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const bool ok = full || base + r * kWarp < a.n;
+      if (ok) {
+        st_stream(w + base + r * kWarp, acc[r]);
+        nacc = fma(acc[r].x, acc[r].x, nacc);
+        nacc = fma(acc[r].y, acc[r].y, nacc);
+      }
+    }
+  }
+
+  __shared__ double s_warp[32];
+  __shared__ int s_last;
+  double s = warp_sum(nacc);
+  if (lane == 0) s_warp[warp] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int k = 0; k < nwarps; ++k) t += s_warp[k];
+    a.npart[blockIdx.x] = t;
+  }
+  if (!last_block_ticket(a.ticket, gridDim.x, &s_last)) return;
+
+  __shared__ double s_red[1];
+  if (warp == 0) {
+    double t = sum_partials(a.npart, gridDim.x, lane);
+    if (lane == 0) s_red[0] = t;
+  }
+  __syncthreads();
+  peer_allreduce(a.comm, s_red, 1, ctl);
+  __syncthreads();
+  if (threadIdx.x == 0) finish_norm(a, s_red[0]);
+}
+
+// ------------------------------------------------------------------ MGS step kernel
+// Kernel i of an MGS sweep (ortho.py:39-41 / :47-50), i = 0..c:
+//   if i > 0:  w -= coef[i-1] * U_{i-1}          (axpy of the previous column)
+//   if i < c:  g_i = <U_i, w>                     (dot with the next column)
+//   if i == 0 and round 1: also ||w||^2           (ortho.py:36)
+//   if i == c: ||w||^2 of the result              (ortho.py:43 / :52)
+template <int R>
+__global__ void __launch_bounds__(256) mgs_step_kernel(OrthoArgs a, int i) {
+  StepCtl* ctl = a.ctl;
+  if (ctl->stop) return;
+  if (a.round == 2 && !ctl->round2) return;
+
+  const int c = a.ncols;
+  const bool do_axpy = i > 0;
+  const bool do_dot = i < c;
+  const bool norm_in = (i == 0);
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nwarps = blockDim.x >> 5;
+  const int64_t ld = a.ld;
+  const cplx* __restrict__ Uprev = a.U + (int64_t)(i - 1) * ld;
+  const cplx* __restrict__ Ucur = a.U + (int64_t)i * ld;
+  cplx* w = a.w;
+  const cplx cf = do_axpy ? a.coef[i - 1] : make_double2(0.0, 0.0);
+
+  cplx dacc = make_double2(0.0, 0.0);
+  double nacc = 0.0;
+  constexpr int ROWS = kWarp * R;
+  const int64_t nchunks = (a.n + ROWS - 1) / ROWS;
+  for (int64_t q = (int64_t)blockIdx.x * nwarps + warp; q < nchunks;
+       q += (int64_t)gridDim.x * nwarps) {
+    const int64_t base = q * ROWS + lane;
+    cplx wv[R], up[R], uc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const bool ok = base + r * kWarp < a.n;
+      wv[r] = ok ? ld_plain(w + base + r * kWarp) : make_double2(0.0, 0.0);
+      up[r] = (ok && do_axpy) ? ld_stream(Uprev + base + r * kWarp) : make_double2(0.0, 0.0);
+      uc[r] = (ok && do_dot) ? ld_stream(Ucur + base + r * kWarp) : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const bool ok = base + r * kWarp < a.n;
+      if (do_axpy) {
+        cfms(wv[r], up[r], cf);
+        if (ok) st_stream(w + base + r * kWarp, wv[r]);
+      }
+      if (do_dot) cfma_conj(dacc, uc[r], wv[r]);
+      if (norm_in || !do_dot) {
+        nacc = fma(wv[r].x, wv[r].x, nacc);
+        nacc = fma(wv[r].y, wv[r].y, nacc);
+      }
+    }
+  }
+
+  __shared__ double s_w[32 * 3];
+  __shared__ int s_last;
+  cplx ds = warp_sum(dacc);
+  double ns = warp_sum(nacc);
+  if (lane == 0) {
+    s_w[warp * 3] = ds.x;
+    s_w[warp * 3 + 1] = ds.y;
+    s_w[warp * 3 + 2] = ns;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double x = 0.0, y = 0.0, t = 0.0;
+    for (int k = 0; k < nwarps; ++k) {
+      x += s_w[k * 3];
+      y += s_w[k * 3 + 1];
+      t += s_w[k * 3 + 2];
+    }
+    a.part[blockIdx.x] = make_double2(x, y);
+    a.npart[blockIdx.x] = t;
+  }
+  if (!last_block_ticket(a.ticket, gridDim.x, &s_last)) return;
+
+  __shared__ double s_red[3];
+  if (warp == 0) {
+    cplx g = sum_partials(a.part, gridDim.x, lane);
+    double t = sum_partials(a.npart, gridDim.x, lane);
+    if (lane == 0) {
+      s_red[0] = g.x;
+      s_red[1] = g.y;
+      s_red[2] = t;
+    }
+  }
+  __syncthreads();
+  peer_allreduce(a.comm, s_red, 3, ctl);
+  __syncthreads();
+  if (do_dot) {
+    // finish_dots expects red[2*ncols] to hold the norm: here ncols == 1
+    finish_dots(a, i, 1, s_red, norm_in && a.round == 1);
+  } else if (threadIdx.x == 0) {
+    finish_norm(a, s_red[2]);
+  }
+}
+
+// ------------------------------------------------------------------ launchers
+static int pick_grid(int64_t work_items, int blocks_per_sm, int num_sms, int cap) {
+  int64_t g = (int64_t)num_sms * blocks_per_sm;
+  if (g > work_items) g = work_items;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// Column-tile width for pass 1: the narrowest tile that keeps the block at <= 16 warps
+// while giving at least 4 warps to hide latency.
+static void pass1_shape(int c, int* ct, int* warps) {
+  int t = (c + 7) / 8;  // aim for ~8 warps
+  if (t < 1) t = 1;
+  if (t > 8) t = 8;
+  int w = (c + t - 1) / t;
+  if (w < 1) w = 1;
+  *ct = t;
+  *warps = w;
+}
+
+template <int CT, int R>
+static cudaError_t launch_pass1_t(const OrthoArgs& a, int warps, int num_sms, cudaStream_t st,
+                                  int grid_mult) {
+  OrthoArgs args = a;
+  const int threads = warps * kWarp;
+  const int64_t nchunks = (a.n + kWarp * R - 1) / (kWarp * R);
+  int bps = grid_mult > 0 ? grid_mult : (threads <= 128 ? 6 : (threads <= 256 ? 4 : 2));
+  const int grid = pick_grid(nchunks, bps, num_sms, a.grid_cap);
+  const size_t smem = sizeof(double) * (2 * a.ncols + 2);
+  cgs_pass1_kernel<CT, R><<<grid, threads, smem, st>>>(args);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_cgs_pass1(const OrthoArgs& a, int num_sms, cudaStream_t st, int grid_mult) {
+  int ct, warps;
+  pass1_shape(a.ncols, &ct, &warps);
+  if (warps > 16) return cudaErrorInvalidValue;
+  switch (ct) {
+    case 1: return launch_pass1_t<1, 4>(a, warps, num_sms, st, grid_mult);
+    case 2: return launch_pass1_t<2, 4>(a, warps, num_sms, st, grid_mult);
+    case 3: return launch_pass1_t<3, 4>(a, warps, num_sms, st, grid_mult);
+    case 4: return launch_pass1_t<4, 4>(a, warps, num_sms, st, grid_mult);
+    case 5: return launch_pass1_t<5, 2>(a, warps, num_sms, st, grid_mult);
+    case 6: return launch_pass1_t<6, 2>(a, warps, num_sms, st, grid_mult);
+    case 7: return launch_pass1_t<7, 2>(a, warps, num_sms, st, grid_mult);
+    default: return launch_pass1_t<8, 2>(a, warps, num_sms, st, grid_mult);
+  }
+}
+
+cudaError_t launch_cgs_pass2(const OrthoArgs& a, int num_sms, cudaStream_t st, int grid_mult) {
+  constexpr int R = 2, UC = 4, THREADS = 256;
+  const int64_t nchunks = (a.n + kWarp * R - 1) / (kWarp * R);
+  const int64_t nblocks = (nchunks + (THREADS / kWarp) - 1) / (THREADS / kWarp);
+  const int grid = pick_grid(nblocks, grid_mult > 0 ? grid_mult : 4, num_sms, a.grid_cap);
+  const size_t smem = sizeof(cplx) * (a.ncols + 1);
+  cgs_pass2_kernel<R, UC><<<grid, THREADS, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_mgs_step(const OrthoArgs& a, int i, int num_sms, cudaStream_t st,
+                            int grid_mult) {
+  constexpr int R = 4, THREADS = 256;
+  const int64_t nchunks = (a.n + kWarp * R - 1) / (kWarp * R);
+  const int64_t nblocks = (nchunks + (THREADS / kWarp) - 1) / (THREADS / kWarp);
+  const int grid = pick_grid(nblocks, grid_mult > 0 ? grid_mult : 4, num_sms, a.grid_cap);
+  mgs_step_kernel<R><<<grid, THREADS, 0, st>>>(a, i);
+  return cudaGetLastError();
+}
+
+}  // namespace ab200

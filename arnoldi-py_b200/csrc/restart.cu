@@ -1,0 +1,147 @@
+// restart.cu -- Krylov-Schur truncation of the basis, in place and in one pass
+// (krylov_schur.py:78 `V[:, :p] = V_active @ Qp` and :81 `V[:, p] = V[:, m]`).
+//
+// Row r of the result depends only on row r of the input, so a block reads the
+// m inputs of its rows, synchronises, and then overwrites the first p+1 columns of
+// the same rows: no second n x p buffer, 16 n (m + p + 2) bytes of traffic.
+// Block = 32 rows (lanes, so each column access of a warp is 512 contiguous bytes)
+// x PW warps; warp y accumulates outputs [y*PT, y*PT+PT) in registers.  The m x p
+// coefficient block (Q with the lazy column scales folded into its rows) sits in
+// shared memory and is read as warp-wide broadcasts.
+#include "kernels.cuh"
+
+namespace ab200 {
+
+template <int PT>
+__global__ void __launch_bounds__(512) restart_kernel(RestartArgs a, int pw) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int m = a.m, p = a.p;
+  // coefficients: shared memory when they fit comfortably, else straight from global
+  // (uniform addresses: one L1-resident broadcast load per warp)
+  const cplx* sq = a.q;  // [m][p]
+  if (pw > 0) {
+    cplx* s = reinterpret_cast<cplx*>(smem_raw);
+    for (int k = threadIdx.x; k < m * p; k += blockDim.x) s[k] = a.q[k];
+    __syncthreads();
+    sq = s;
+  }
+
+  const int lane = threadIdx.x & 31;
+  const int wy = threadIdx.x >> 5;
+  const int k0 = wy * PT;
+  int nk = p - k0;
+  nk = nk < 0 ? 0 : (nk > PT ? PT : nk);
+  const int64_t ld = a.ld;
+  const int64_t nchunks = (a.n + kWarp - 1) / kWarp;
+
+  for (int64_t q = blockIdx.x; q < nchunks; q += gridDim.x) {
+    const int64_t row = q * kWarp + lane;
+    const bool ok = row < a.n;
+    const cplx* src = a.U + (ok ? row : 0);  // coherent loads: U is also written here
+    cplx acc[PT];
+#pragma unroll
+    for (int k = 0; k < PT; ++k) acc[k] = make_double2(0.0, 0.0);
+    int i = 0;
+    for (; i + 4 <= m; i += 4) {
+      cplx u[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) u[t] = src[(int64_t)(i + t) * ld];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const cplx* qrow = sq + (i + t) * p + k0;
+#pragma unroll
+        for (int k = 0; k < PT; ++k)
+          if (k < nk) cfma(acc[k], u[t], qrow[k]);
+      }
+    }
+    for (; i < m; ++i) {
+      const cplx u = src[(int64_t)i * ld];
+      const cplx* qrow = sq + i * p + k0;
+#pragma unroll
+      for (int k = 0; k < PT; ++k)
+        if (k < nk) cfma(acc[k], u, qrow[k]);
+    }
+    cplx tail = make_double2(0.0, 0.0);
+    if (wy == 0) tail = cscale(src[(int64_t)m * ld], a.scale_m);
+    __syncthreads();  // every warp of the block has read its inputs for these rows
+    if (ok) {
+      cplx* dst = a.U + row;
+#pragma unroll
+      for (int k = 0; k < PT; ++k)
+        if (k < nk) st_stream(dst + (int64_t)(k0 + k) * ld, acc[k]);
+      if (wy == 0) st_stream(dst + (int64_t)p * ld, tail);
+    }
+  }
+}
+
+template <int PT>
+static cudaError_t launch_restart_t(const RestartArgs& a, int num_sms, cudaStream_t st) {
+  const int nw = (a.p + PT - 1) / PT;
+  const int threads = nw * kWarp;
+  size_t smem = sizeof(cplx) * (size_t)a.m * a.p;
+  int pw = 1;  // 1: stage the coefficients in shared memory
+  if (smem > 100 * 1024) {
+    smem = 0;
+    pw = 0;
+  }
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(restart_kernel<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         200 * 1024);
+    attr_done = true;
+  }
+  const int64_t nchunks = (a.n + kWarp - 1) / kWarp;
+  int bps = 2048 / threads;
+  if (bps > 8) bps = 8;
+  if (bps < 1) bps = 1;
+  int64_t grid = (int64_t)num_sms * bps;
+  if (grid > nchunks) grid = nchunks;
+  if (grid < 1) grid = 1;
+  restart_kernel<PT><<<(int)grid, threads, smem, st>>>(a, pw);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_restart(const RestartArgs& a, int num_sms, cudaStream_t st, int variant) {
+  // PT outputs per warp; at most 16 warps per block
+  int pt = variant > 0 ? variant : 8;
+  while ((a.p + pt - 1) / pt > 16) pt *= 2;
+  if (pt <= 4) return launch_restart_t<4>(a, num_sms, st);
+  if (pt <= 8) return launch_restart_t<8>(a, num_sms, st);
+  if (pt <= 16) return launch_restart_t<16>(a, num_sms, st);
+  return cudaErrorInvalidValue;
+}
+
+// ------------------------------------------------------------------ materialise scales
+__global__ void __launch_bounds__(256) materialize_kernel(cplx* U, int64_t n, int64_t ld, int col0,
+                                                          int ncols, double* scale) {
+  for (int c = 0; c < ncols; ++c) {
+    const double s = scale[col0 + c];
+    if (s == 1.0) continue;
+    cplx* col = U + (int64_t)(col0 + c) * ld;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n;
+         r += (int64_t)gridDim.x * blockDim.x)
+      col[r] = cscale(col[r], s);
+  }
+}
+__global__ void reset_scale_kernel(double* scale, int col0, int ncols) {
+  const int i = threadIdx.x;
+  if (i < ncols) scale[col0 + i] = 1.0;
+}
+
+cudaError_t launch_materialize(cplx* U, int64_t n, int64_t ld, int col0, int ncols, double* scale,
+                               int num_sms, cudaStream_t st) {
+  if (ncols <= 0) return cudaSuccess;
+  int64_t grid = (n + 255) / 256;
+  if (grid > (int64_t)num_sms * 8) grid = (int64_t)num_sms * 8;
+  if (grid < 1) grid = 1;
+  materialize_kernel<<<(int)grid, 256, 0, st>>>(U, n, ld, col0, ncols, scale);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  for (int c0 = 0; c0 < ncols; c0 += 256) {
+    const int nc = ncols - c0 < 256 ? ncols - c0 : 256;
+    reset_scale_kernel<<<1, 256, 0, st>>>(scale, col0 + c0, nc);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace ab200

@@ -1,0 +1,680 @@
+// solver.cu -- the C ABI declared in include/arnoldi_b200.h.
+//
+// One ab200_solver owns, on one GPU: the Krylov basis (column-major complex128,
+// un-normalised columns + a lazy scale per column), the CSR block of A, the device
+// copy of H, the reduction scratch and a control block.  ab200_expand enqueues a
+// whole Arnoldi expansion (decomposition.py:56-66) without a host round trip and
+// synchronises once at the end to hand the new columns of H to the host driver.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/arnoldi_b200.h"
+#include "kernels.cuh"
+
+using namespace ab200;
+
+// ---------------------------------------------------------------------------- errors
+static thread_local char g_err[512] = "";
+static int set_err(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CU(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t e__ = (call);                                                             \
+    if (e__ != cudaSuccess)                                                               \
+      return set_err(e__ == cudaErrorMemoryAllocation ? AB200_ENOMEM : AB200_ECUDA,       \
+                     "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__,   \
+                     __LINE__);                                                           \
+  } while (0)
+#define REQUIRE(cond, ...) \
+  do {                     \
+    if (!(cond)) return set_err(AB200_EINVAL, __VA_ARGS__); \
+  } while (0)
+
+// ---------------------------------------------------------------------------- solver
+enum KClass { K_SPMV = 0, K_PASS1, K_PASS2, K_MGS, K_RESTART, K_OTHER, K_NCLASS };
+
+struct TimedLaunch {
+  int cls;
+  int step;   // Arnoldi step j (or -1)
+  int round;  // 1, 2 or 0
+  double bytes;
+  cudaEvent_t a, b;
+};
+
+struct ab200_solver {
+  int device = 0;
+  int num_sms = kNumSMsB200;
+  int64_t n_global = 0, row0 = 0, n = 0, ld = 0;
+  int max_dim = 0;
+  cudaStream_t stream = nullptr;
+
+  cplx* V = nullptr;       // ld x (max_dim + 1)
+  cplx* wtmp = nullptr;    // n-length scratch (stand-alone ortho / spmv output)
+  cplx* xtmp = nullptr;    // n_global-length scratch (stand-alone spmv input)
+  double* scale = nullptr;  // [max_dim + 1]
+  cplx* Hdev = nullptr;    // (max_dim + 1) x max_dim column-major
+  cplx* hscratch = nullptr;  // [max_dim + 2] h column for the stand-alone ortho
+  cplx* coef = nullptr;    // [max_dim + 1]
+  cplx* part = nullptr;    // [(max_dim + 1) * grid_cap]
+  double* npart = nullptr;  // [grid_cap]
+  unsigned* ticket = nullptr;
+  StepCtl* ctl = nullptr;
+  int* step_round2 = nullptr;  // [max_dim] 1 when step j ran the second round
+  cplx* qdev = nullptr;    // [max_dim * max_dim] restart coefficients
+  int grid_cap = 0;
+
+  // pinned host mirrors
+  cplx* h_H = nullptr;
+  double* h_scale = nullptr;
+  StepCtl* h_ctl = nullptr;
+  int* h_step_round2 = nullptr;
+  cplx* h_q = nullptr;
+
+  // CSR block
+  void* indptr = nullptr;
+  int indptr_bits = 32;
+  int32_t* indices = nullptr;
+  void* values = nullptr;
+  int value_kind = AB200_F64;
+  int64_t nnz = -1;
+  int64_t* rowblk = nullptr;
+  int nblk = 0;
+  int tile = 0;
+  cplx* ghost = nullptr;
+  int64_t n_local_cols = 0;
+
+  PeerComm comm;
+
+  // options
+  int opt_grid_mult = 0, opt_restart_variant = 0, opt_ortho_variant = 0, opt_spmv_tile = 0;
+
+  // stats
+  bool timing = false;
+  std::vector<TimedLaunch> pending;
+  std::vector<cudaEvent_t> pool;
+  ab200_stats st;
+  bool has_basis_data = false;
+};
+
+static cudaEvent_t get_event(ab200_solver* s) {
+  if (!s->pool.empty()) {
+    cudaEvent_t e = s->pool.back();
+    s->pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+
+struct LaunchScope {
+  ab200_solver* s;
+  TimedLaunch t;
+  bool on;
+  LaunchScope(ab200_solver* s_, int cls, int step, int round, double bytes) : s(s_) {
+    on = s->timing;
+    t.cls = cls;
+    t.step = step;
+    t.round = round;
+    t.bytes = bytes;
+    if (on) {
+      t.a = get_event(s);
+      t.b = get_event(s);
+      cudaEventRecord(t.a, s->stream);
+    } else {
+      t.a = t.b = nullptr;
+    }
+  }
+  ~LaunchScope() {
+    if (on) cudaEventRecord(t.b, s->stream);
+    s->pending.push_back(t);
+    s->st.kernel_launches += 1;
+  }
+};
+
+// fold pending launches into the stats; the stream must be idle
+static void resolve_pending(ab200_solver* s, const int* step_round2 /* may be null */) {
+  for (auto& t : s->pending) {
+    bool executed = true;
+    if (t.round == 2 && t.step >= 0 && step_round2 != nullptr && !step_round2[t.step])
+      executed = false;
+    if (t.step >= 0 && s->h_ctl && s->h_ctl->stop && t.step > s->h_ctl->broke_at) executed = false;
+    float ms = 0.f;
+    if (t.a) {
+      cudaEventElapsedTime(&ms, t.a, t.b);
+      s->pool.push_back(t.a);
+      s->pool.push_back(t.b);
+    }
+    if (!executed) continue;
+    switch (t.cls) {
+      case K_SPMV:
+        s->st.spmv_ms += ms, s->st.spmv_bytes += t.bytes, s->st.spmv_launches++;
+        break;
+      case K_PASS1:
+        s->st.ortho_pass1_ms += ms, s->st.ortho_pass1_bytes += t.bytes,
+            s->st.ortho_pass1_launches++;
+        break;
+      case K_PASS2:
+        s->st.ortho_pass2_ms += ms, s->st.ortho_pass2_bytes += t.bytes,
+            s->st.ortho_pass2_launches++;
+        break;
+      case K_MGS:
+        s->st.mgs_ms += ms, s->st.mgs_bytes += t.bytes, s->st.mgs_launches++;
+        break;
+      case K_RESTART:
+        s->st.restart_ms += ms, s->st.restart_bytes += t.bytes, s->st.restart_launches++;
+        break;
+      default:
+        break;
+    }
+  }
+  s->pending.clear();
+}
+
+__global__ void init_ctl_kernel(StepCtl* ctl, double* scale, int nscale, bool reset_counters) {
+  if (threadIdx.x == 0) {
+    ctl->stop = 0;
+    ctl->broke_at = -1;
+    ctl->round2 = 0;
+    ctl->comm_error = 0;
+    if (reset_counters) {
+      ctl->rounds_total = 0;
+      ctl->second_total = 0;
+      ctl->steps_total = 0;
+    }
+    ctl->nrm0sq = 0.0;
+    ctl->beta = 0.0;
+  }
+  if (scale != nullptr)
+    for (int i = threadIdx.x; i < nscale; i += blockDim.x) scale[i] = 1.0;
+}
+__global__ void set_scale_kernel(double* scale, int col0, int ncols, double v) {
+  for (int i = threadIdx.x; i < ncols; i += blockDim.x) scale[col0 + i] = v;
+}
+
+static OrthoArgs make_ortho_args(ab200_solver* s, cplx* w, int ncols, int j, double tol, double eta,
+                                 cplx* hcol, int finalize) {
+  OrthoArgs a;
+  a.U = s->V;
+  a.w = w;
+  a.n = s->n;
+  a.ld = s->ld;
+  a.ncols = ncols;
+  a.j = j;
+  a.round = 1;
+  a.accumulate = 0;
+  a.finalize = finalize;
+  a.grid_cap = s->grid_cap;
+  a.tol = tol;
+  a.eta = eta;
+  a.scale = s->scale;
+  a.hcol = hcol;
+  a.coef = s->coef;
+  a.part = s->part;
+  a.npart = s->npart;
+  a.ticket = s->ticket;
+  a.ctl = s->ctl;
+  a.step_flag = nullptr;
+  a.comm = s->comm;
+  return a;
+}
+
+// enqueue one orthogonalisation (both possible rounds) of w against U[:, :ncols]
+static int enqueue_ortho(ab200_solver* s, OrthoArgs a, int ortho_kind) {
+  const double nb = 16.0 * (double)s->n;
+  const int c = a.ncols;
+  for (int round = 1; round <= 2; ++round) {
+    a.round = round;
+    a.accumulate = (round == 2);
+    if (ortho_kind == AB200_ORTHO_CGS2) {
+      {
+        LaunchScope ls(s, K_PASS1, a.j, round, nb * (c + 1));
+        CU(launch_cgs_pass1(a, s->num_sms, s->stream, s->opt_grid_mult));
+      }
+      {
+        LaunchScope ls(s, K_PASS2, a.j, round, nb * (c + 2));
+        CU(launch_cgs_pass2(a, s->num_sms, s->stream, s->opt_grid_mult));
+      }
+    } else {
+      for (int i = 0; i <= c; ++i) {
+        // kernel i touches w (read, and written when i > 0), U_{i-1} and U_i
+        double vecs = 1.0 + (i > 0 ? 2.0 : 0.0) + (i < c ? 1.0 : 0.0);
+        LaunchScope ls(s, K_MGS, a.j, round, nb * vecs);
+        CU(launch_mgs_step(a, i, s->num_sms, s->stream, s->opt_grid_mult));
+      }
+    }
+  }
+  return AB200_OK;
+}
+
+// ---------------------------------------------------------------------------- ABI
+extern "C" {
+
+int ab200_abi_version(void) { return AB200_ABI_VERSION; }
+const char* ab200_last_error(void) { return g_err; }
+
+int ab200_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) return set_err(AB200_ECUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+  return n;
+}
+
+int ab200_destroy(ab200_solver* s) {
+  if (!s) return AB200_OK;
+  cudaSetDevice(s->device);
+  if (s->stream) cudaStreamSynchronize(s->stream);
+  resolve_pending(s, nullptr);
+  for (auto e : s->pool) cudaEventDestroy(e);
+  cudaFree(s->V), cudaFree(s->wtmp), cudaFree(s->xtmp), cudaFree(s->scale), cudaFree(s->Hdev);
+  cudaFree(s->hscratch), cudaFree(s->coef), cudaFree(s->part), cudaFree(s->npart);
+  cudaFree(s->ticket), cudaFree(s->ctl), cudaFree(s->step_round2), cudaFree(s->qdev);
+  cudaFree(s->indptr), cudaFree(s->indices), cudaFree(s->values), cudaFree(s->rowblk);
+  cudaFree(s->ghost);
+  cudaFreeHost(s->h_H), cudaFreeHost(s->h_scale), cudaFreeHost(s->h_ctl);
+  cudaFreeHost(s->h_step_round2), cudaFreeHost(s->h_q);
+  if (s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+  return AB200_OK;
+}
+
+int ab200_create(ab200_solver** out, int device, int64_t n_global, int64_t row0,
+                 int64_t nrows_local, int max_dim) {
+  REQUIRE(out != nullptr, "out is null");
+  *out = nullptr;
+  REQUIRE(n_global > 0 && nrows_local > 0 && row0 >= 0 && row0 + nrows_local <= n_global,
+          "bad row block: n_global=%lld row0=%lld nrows_local=%lld", (long long)n_global,
+          (long long)row0, (long long)nrows_local);
+  REQUIRE(max_dim >= 1 && max_dim <= 128, "max_dim must be in [1, 128], got %d", max_dim);
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  REQUIRE(device >= 0 && device < ndev, "device %d not available (%d visible)", device, ndev);
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return set_err(AB200_ECUDA, "device %d is sm_%d%d; this library is built for sm_100a only",
+                   device, prop.major, prop.minor);
+
+  ab200_solver* s = new ab200_solver();
+  memset(&s->st, 0, sizeof(s->st));
+  memset(&s->comm, 0, sizeof(s->comm));
+  s->comm.nranks = 1;
+  s->device = device;
+  s->num_sms = prop.multiProcessorCount;
+  s->n_global = n_global;
+  s->row0 = row0;
+  s->n = nrows_local;
+  s->n_local_cols = nrows_local;
+  s->ld = (nrows_local + 7) / 8 * 8;  // columns start on 128-byte lines
+  s->max_dim = max_dim;
+  s->grid_cap = s->num_sms * 8;
+  const int md1 = max_dim + 1;
+#define CUX(call)                                   \
+  do {                                              \
+    cudaError_t e__ = (call);                       \
+    if (e__ != cudaSuccess) {                       \
+      int rc__ = set_err(e__ == cudaErrorMemoryAllocation ? AB200_ENOMEM : AB200_ECUDA, \
+                         "%s failed: %s", #call, cudaGetErrorString(e__));              \
+      ab200_destroy(s);                             \
+      return rc__;                                  \
+    }                                               \
+  } while (0)
+  CUX(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  CUX(cudaMalloc(&s->V, sizeof(cplx) * (size_t)s->ld * md1));
+  CUX(cudaMalloc(&s->wtmp, sizeof(cplx) * (size_t)s->ld));
+  CUX(cudaMalloc(&s->scale, sizeof(double) * md1));
+  CUX(cudaMalloc(&s->Hdev, sizeof(cplx) * (size_t)md1 * max_dim));
+  CUX(cudaMalloc(&s->hscratch, sizeof(cplx) * (md1 + 1)));
+  CUX(cudaMalloc(&s->coef, sizeof(cplx) * md1));
+  CUX(cudaMalloc(&s->part, sizeof(cplx) * (size_t)md1 * s->grid_cap));
+  CUX(cudaMalloc(&s->npart, sizeof(double) * s->grid_cap));
+  CUX(cudaMalloc(&s->ticket, sizeof(unsigned)));
+  CUX(cudaMalloc(&s->ctl, sizeof(StepCtl)));
+  CUX(cudaMalloc(&s->step_round2, sizeof(int) * max_dim));
+  CUX(cudaMalloc(&s->qdev, sizeof(cplx) * (size_t)max_dim * max_dim));
+  CUX(cudaMallocHost(&s->h_H, sizeof(cplx) * (size_t)md1 * max_dim));
+  CUX(cudaMallocHost(&s->h_scale, sizeof(double) * md1));
+  CUX(cudaMallocHost(&s->h_ctl, sizeof(StepCtl)));
+  CUX(cudaMallocHost(&s->h_step_round2, sizeof(int) * max_dim));
+  CUX(cudaMallocHost(&s->h_q, sizeof(cplx) * (size_t)max_dim * max_dim));
+  // krylov_schur.py:42-43: V and H start as zeros
+  CUX(cudaMemsetAsync(s->V, 0, sizeof(cplx) * (size_t)s->ld * md1, s->stream));
+  CUX(cudaMemsetAsync(s->wtmp, 0, sizeof(cplx) * (size_t)s->ld, s->stream));
+  CUX(cudaMemsetAsync(s->Hdev, 0, sizeof(cplx) * (size_t)md1 * max_dim, s->stream));
+  CUX(cudaMemsetAsync(s->ticket, 0, sizeof(unsigned), s->stream));
+  CUX(cudaMemsetAsync(s->step_round2, 0, sizeof(int) * max_dim, s->stream));
+  init_ctl_kernel<<<1, 128, 0, s->stream>>>(s->ctl, s->scale, md1, true);
+  CUX(cudaGetLastError());
+  CUX(cudaStreamSynchronize(s->stream));
+  for (int i = 0; i < md1; ++i) s->h_scale[i] = 1.0;
+  memset(s->h_ctl, 0, sizeof(StepCtl));
+  s->h_ctl->broke_at = -1;
+#undef CUX
+  *out = s;
+  return AB200_OK;
+}
+
+int ab200_set_csr(ab200_solver* s, const void* indptr, int indptr_bits, const int32_t* indices,
+                  const void* values, int value_kind, int64_t nnz, int spmv_algo) {
+  REQUIRE(s != nullptr, "solver is null");
+  REQUIRE(indptr_bits == 32 || indptr_bits == 64, "indptr_bits must be 32 or 64");
+  REQUIRE(value_kind == AB200_F64 || value_kind == AB200_C128, "bad value_kind %d", value_kind);
+  REQUIRE(nnz >= 0, "nnz < 0");
+  REQUIRE(indptr != nullptr && (nnz == 0 || (indices != nullptr && values != nullptr)),
+          "null CSR array");
+  REQUIRE(spmv_algo >= AB200_SPMV_AUTO && spmv_algo <= AB200_SPMV_MERGE, "bad spmv_algo");
+  const int64_t first = indptr_bits == 32 ? ((const int32_t*)indptr)[0] : ((const int64_t*)indptr)[0];
+  const int64_t last =
+      indptr_bits == 32 ? ((const int32_t*)indptr)[s->n] : ((const int64_t*)indptr)[s->n];
+  REQUIRE(first == 0 && last == nnz, "indptr[0]=%lld, indptr[n]=%lld, nnz=%lld: not a CSR block",
+          (long long)first, (long long)last, (long long)nnz);
+  CU(cudaSetDevice(s->device));
+  CU(cudaStreamSynchronize(s->stream));
+  cudaFree(s->indptr), cudaFree(s->indices), cudaFree(s->values), cudaFree(s->rowblk);
+  s->indptr = s->indices = nullptr, s->values = nullptr, s->rowblk = nullptr;
+  s->nnz = -1;
+  const size_t ipb = (size_t)indptr_bits / 8, vb = value_kind == AB200_F64 ? 8 : 16;
+  CU(cudaMalloc(&s->indptr, ipb * (s->n + 1)));
+  CU(cudaMalloc(&s->indices, sizeof(int32_t) * (size_t)(nnz + 4)));
+  CU(cudaMalloc(&s->values, vb * (size_t)(nnz + 4)));
+  CU(cudaMemcpyAsync(s->indptr, indptr, ipb * (s->n + 1), cudaMemcpyHostToDevice, s->stream));
+  if (nnz > 0) {
+    CU(cudaMemcpyAsync(s->indices, indices, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice,
+                       s->stream));
+    CU(cudaMemcpyAsync(s->values, values, vb * (size_t)nnz, cudaMemcpyHostToDevice, s->stream));
+  }
+  // nnz tile: about one row per thread of a 256-thread block, within [512, 2048]
+  int tile = s->opt_spmv_tile;
+  if (tile <= 0) {
+    double avg = (double)nnz / (double)s->n;
+    tile = (int)(avg * 256.0);
+    tile = (tile + 255) / 256 * 256;
+    if (tile < 512) tile = 512;
+    if (tile > 2048) tile = 2048;
+  }
+  int64_t nblk = (nnz + tile - 1) / tile;
+  if (nblk < 1) nblk = 1;
+  REQUIRE(nblk < (1ll << 30), "too many SpMV tiles");
+  CU(cudaMalloc(&s->rowblk, sizeof(int64_t) * (size_t)(nblk + 1)));
+  CU(launch_spmv_plan(s->indptr, indptr_bits, s->n, nnz, tile, (int)nblk, s->rowblk, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  s->indptr_bits = indptr_bits;
+  s->value_kind = value_kind;
+  s->nnz = nnz;
+  s->tile = tile;
+  s->nblk = (int)nblk;
+  return AB200_OK;
+}
+
+int ab200_set_columns(ab200_solver* s, int col0, int ncols, const double* host, int64_t ld_host) {
+  REQUIRE(s != nullptr && host != nullptr, "null argument");
+  REQUIRE(col0 >= 0 && ncols >= 1 && col0 + ncols <= s->max_dim + 1, "column range [%d, %d) out of [0, %d]",
+          col0, col0 + ncols, s->max_dim + 1);
+  REQUIRE(ld_host >= s->n, "ld_host < nrows_local");
+  CU(cudaSetDevice(s->device));
+  CU(cudaMemcpy2DAsync(s->V + (size_t)col0 * s->ld, sizeof(cplx) * s->ld, host,
+                       sizeof(cplx) * ld_host, sizeof(cplx) * s->n, ncols, cudaMemcpyHostToDevice,
+                       s->stream));
+  set_scale_kernel<<<1, 128, 0, s->stream>>>(s->scale, col0, ncols, 1.0);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(s->stream));
+  for (int i = 0; i < ncols; ++i) s->h_scale[col0 + i] = 1.0;
+  return AB200_OK;
+}
+
+int ab200_get_columns(ab200_solver* s, int col0, int ncols, double* host, int64_t ld_host) {
+  REQUIRE(s != nullptr && host != nullptr, "null argument");
+  REQUIRE(col0 >= 0 && ncols >= 1 && col0 + ncols <= s->max_dim + 1, "column range [%d, %d) out of [0, %d]",
+          col0, col0 + ncols, s->max_dim + 1);
+  REQUIRE(ld_host >= s->n, "ld_host < nrows_local");
+  CU(cudaSetDevice(s->device));
+  // apply the lazy scales in place first (a no-op for columns whose scale is 1)
+  CU(launch_materialize(s->V, s->n, s->ld, col0, ncols, s->scale, s->num_sms, s->stream));
+  s->st.kernel_launches += 2;
+  CU(cudaMemcpy2DAsync(host, sizeof(cplx) * ld_host, s->V + (size_t)col0 * s->ld,
+                       sizeof(cplx) * s->ld, sizeof(cplx) * s->n, ncols, cudaMemcpyDeviceToHost,
+                       s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  for (int i = 0; i < ncols; ++i) s->h_scale[col0 + i] = 1.0;
+  return AB200_OK;
+}
+
+static int enqueue_spmv(ab200_solver* s, const cplx* x, cplx* y, const double* xscale, int step,
+                        bool in_expand) {
+  SpmvArgs a;
+  a.indptr = s->indptr;
+  a.indices = s->indices;
+  a.values = s->values;
+  a.rowblk = s->rowblk;
+  a.x = x;
+  a.ghost = s->ghost;
+  a.y = y;
+  a.xscale = xscale;
+  a.n = s->n;
+  a.n_local_cols = s->n_local_cols;
+  a.nblocks = s->nblk;
+  a.tile = s->tile;
+  a.ctl = in_expand ? s->ctl : nullptr;
+  const double sv = s->value_kind == AB200_F64 ? 8.0 : 16.0;
+  const double bytes = (double)s->nnz * (sv + 4.0) + (double)s->n * (s->indptr_bits / 8 + 32.0);
+  LaunchScope ls(s, K_SPMV, step, 0, bytes);
+  CU(launch_spmv(a, s->indptr_bits, s->value_kind, s->stream));
+  return AB200_OK;
+}
+
+int ab200_expand(ab200_solver* s, int start_dim, int end_dim, double tol, double eta,
+                 int ortho_kind, double* h_cols, int* n_iter, int* breakdown) {
+  REQUIRE(s != nullptr && h_cols != nullptr && n_iter != nullptr && breakdown != nullptr,
+          "null argument");
+  REQUIRE(0 <= start_dim && start_dim <= end_dim && end_dim <= s->max_dim,
+          "need 0 <= start_dim (%d) <= end_dim (%d) <= max_dim (%d)", start_dim, end_dim,
+          s->max_dim);
+  REQUIRE(ortho_kind == AB200_ORTHO_CGS2 || ortho_kind == AB200_ORTHO_MGS, "bad ortho_kind %d",
+          ortho_kind);
+  if (s->nnz < 0) return set_err(AB200_ESTATE, "ab200_expand called before ab200_set_csr");
+  CU(cudaSetDevice(s->device));
+  const int md1 = s->max_dim + 1;
+  init_ctl_kernel<<<1, 32, 0, s->stream>>>(s->ctl, nullptr, 0, false);
+  CU(cudaGetLastError());
+  s->st.kernel_launches += 1;
+  for (int j = start_dim; j < end_dim; ++j) {
+    cplx* x = s->V + (size_t)j * s->ld;
+    cplx* w = s->V + (size_t)(j + 1) * s->ld;
+    int rc = enqueue_spmv(s, x, w, s->scale + j, j, true);  // decomposition.py:57-58
+    if (rc != AB200_OK) return rc;
+    OrthoArgs a = make_ortho_args(s, w, j + 1, j, tol, eta, s->Hdev + (size_t)j * md1, 1);
+    a.step_flag = s->step_round2 + j;
+    rc = enqueue_ortho(s, a, ortho_kind);  // decomposition.py:60
+    if (rc != AB200_OK) return rc;
+  }
+  if (end_dim > start_dim) {
+    CU(cudaMemcpyAsync(s->h_H + (size_t)start_dim * md1, s->Hdev + (size_t)start_dim * md1,
+                       sizeof(cplx) * (size_t)md1 * (end_dim - start_dim), cudaMemcpyDeviceToHost,
+                       s->stream));
+    CU(cudaMemcpyAsync(s->h_step_round2, s->step_round2, sizeof(int) * s->max_dim,
+                       cudaMemcpyDeviceToHost, s->stream));
+  }
+  CU(cudaMemcpyAsync(s->h_scale, s->scale, sizeof(double) * md1, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaMemcpyAsync(s->h_ctl, s->ctl, sizeof(StepCtl), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  resolve_pending(s, s->h_step_round2);
+  if (s->h_ctl->comm_error) return set_err(AB200_ECOMM, "peer reduction timed out");
+  int done = end_dim;
+  *breakdown = 0;
+  if (s->h_ctl->stop) {
+    done = s->h_ctl->broke_at + 1;
+    *breakdown = 1;
+  }
+  *n_iter = done;
+  cplx* hc = reinterpret_cast<cplx*>(h_cols);
+  for (int j = start_dim; j < done; ++j) {
+    const bool broke = (*breakdown && j == done - 1);
+    const int rows = broke ? j + 1 : j + 2;
+    memcpy(hc + (size_t)j * md1, s->h_H + (size_t)j * md1, sizeof(cplx) * rows);
+  }
+  s->st.arnoldi_steps = s->h_ctl->steps_total;
+  s->st.ortho_rounds = s->h_ctl->rounds_total;
+  s->st.second_rounds = s->h_ctl->second_total;
+  return AB200_OK;
+}
+
+int ab200_restart(ab200_solver* s, const double* q, int64_t ldq, int m, int p) {
+  REQUIRE(s != nullptr && q != nullptr, "null argument");
+  REQUIRE(m >= 1 && m <= s->max_dim && p >= 1 && p < m, "need 1 <= p (%d) < m (%d) <= max_dim (%d)", p,
+          m, s->max_dim);
+  REQUIRE(ldq >= m, "ldq < m");
+  CU(cudaSetDevice(s->device));
+  // fold the lazy column scales into the rows of Q:  V_i = scale[i] U_i
+  const cplx* qh = reinterpret_cast<const cplx*>(q);
+  for (int i = 0; i < m; ++i)
+    for (int k = 0; k < p; ++k) {
+      const cplx v = qh[(size_t)k * ldq + i];
+      s->h_q[(size_t)i * p + k] = make_double2(v.x * s->h_scale[i], v.y * s->h_scale[i]);
+    }
+  CU(cudaMemcpyAsync(s->qdev, s->h_q, sizeof(cplx) * (size_t)m * p, cudaMemcpyHostToDevice,
+                     s->stream));
+  RestartArgs a;
+  a.U = s->V;
+  a.n = s->n;
+  a.ld = s->ld;
+  a.m = m;
+  a.p = p;
+  a.q = s->qdev;
+  a.scale_m = s->h_scale[m];
+  {
+    LaunchScope ls(s, K_RESTART, -1, 0, 16.0 * (double)s->n * (m + p + 2));
+    CU(launch_restart(a, s->num_sms, s->stream, s->opt_restart_variant));
+  }
+  set_scale_kernel<<<1, 128, 0, s->stream>>>(s->scale, 0, p + 1, 1.0);
+  CU(cudaGetLastError());
+  s->st.kernel_launches += 1;
+  CU(cudaStreamSynchronize(s->stream));
+  for (int i = 0; i <= p; ++i) s->h_scale[i] = 1.0;
+  resolve_pending(s, nullptr);
+  return AB200_OK;
+}
+
+int ab200_spmv(ab200_solver* s, const double* x_host, double* y_host) {
+  REQUIRE(s != nullptr && x_host != nullptr && y_host != nullptr, "null argument");
+  if (s->nnz < 0) return set_err(AB200_ESTATE, "ab200_spmv called before ab200_set_csr");
+  if (s->n != s->n_global)
+    return set_err(AB200_ESTATE, "ab200_spmv is a single-GPU entry point (row block is partial)");
+  CU(cudaSetDevice(s->device));
+  if (!s->xtmp) CU(cudaMalloc(&s->xtmp, sizeof(cplx) * (size_t)s->n_global));
+  CU(cudaMemcpyAsync(s->xtmp, x_host, sizeof(cplx) * (size_t)s->n_global, cudaMemcpyHostToDevice,
+                     s->stream));
+  int rc = enqueue_spmv(s, s->xtmp, s->wtmp, nullptr, -1, false);
+  if (rc != AB200_OK) return rc;
+  CU(cudaMemcpyAsync(y_host, s->wtmp, sizeof(cplx) * (size_t)s->n, cudaMemcpyDeviceToHost,
+                     s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  resolve_pending(s, nullptr);
+  return AB200_OK;
+}
+
+int ab200_ortho(ab200_solver* s, int ncols, double* w_host, double* h_host, double tol, double eta,
+                int ortho_kind, double* beta, int* breakdown) {
+  REQUIRE(s != nullptr && w_host != nullptr && h_host != nullptr && beta != nullptr &&
+              breakdown != nullptr,
+          "null argument");
+  REQUIRE(ncols >= 1 && ncols <= s->max_dim, "ncols (%d) must be in [1, max_dim=%d]", ncols,
+          s->max_dim);
+  REQUIRE(ortho_kind == AB200_ORTHO_CGS2 || ortho_kind == AB200_ORTHO_MGS, "bad ortho_kind %d",
+          ortho_kind);
+  CU(cudaSetDevice(s->device));
+  CU(cudaMemcpyAsync(s->wtmp, w_host, sizeof(cplx) * (size_t)s->n, cudaMemcpyHostToDevice,
+                     s->stream));
+  CU(cudaMemsetAsync(s->hscratch, 0, sizeof(cplx) * (s->max_dim + 2), s->stream));
+  init_ctl_kernel<<<1, 32, 0, s->stream>>>(s->ctl, nullptr, 0, false);
+  CU(cudaGetLastError());
+  s->st.kernel_launches += 1;
+  OrthoArgs a = make_ortho_args(s, s->wtmp, ncols, ncols - 1, tol, eta, s->hscratch, 0);
+  int rc = enqueue_ortho(s, a, ortho_kind);
+  if (rc != AB200_OK) return rc;
+  CU(cudaMemcpyAsync(w_host, s->wtmp, sizeof(cplx) * (size_t)s->n, cudaMemcpyDeviceToHost,
+                     s->stream));
+  CU(cudaMemcpyAsync(s->h_H, s->hscratch, sizeof(cplx) * ncols, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaMemcpyAsync(s->h_ctl, s->ctl, sizeof(StepCtl), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  // stand-alone call: every enqueued round-2 launch is attributed by the second_total delta
+  int r2 = s->h_ctl->second_total > s->st.second_rounds ? 1 : 0;
+  std::vector<int> flags(s->max_dim, r2);
+  resolve_pending(s, flags.data());
+  if (s->h_ctl->comm_error) return set_err(AB200_ECOMM, "peer reduction timed out");
+  memcpy(h_host, s->h_H, sizeof(cplx) * ncols);
+  *beta = s->h_ctl->beta;
+  *breakdown = (*beta < tol) ? 1 : 0;
+  s->st.ortho_rounds = s->h_ctl->rounds_total;
+  s->st.second_rounds = s->h_ctl->second_total;
+  return AB200_OK;
+}
+
+int ab200_set_timing(ab200_solver* s, int enabled) {
+  REQUIRE(s != nullptr, "solver is null");
+  s->timing = enabled != 0;
+  return AB200_OK;
+}
+
+int ab200_reset_stats(ab200_solver* s) {
+  REQUIRE(s != nullptr, "solver is null");
+  CU(cudaSetDevice(s->device));
+  CU(cudaStreamSynchronize(s->stream));
+  resolve_pending(s, nullptr);
+  memset(&s->st, 0, sizeof(s->st));
+  init_ctl_kernel<<<1, 32, 0, s->stream>>>(s->ctl, nullptr, 0, true);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(s->stream));
+  return AB200_OK;
+}
+
+int ab200_get_stats(ab200_solver* s, ab200_stats* out) {
+  REQUIRE(s != nullptr && out != nullptr, "null argument");
+  *out = s->st;
+  return AB200_OK;
+}
+
+int ab200_synchronize(ab200_solver* s) {
+  REQUIRE(s != nullptr, "solver is null");
+  CU(cudaSetDevice(s->device));
+  CU(cudaStreamSynchronize(s->stream));
+  return AB200_OK;
+}
+
+int ab200_set_option(ab200_solver* s, const char* key, int64_t value) {
+  REQUIRE(s != nullptr && key != nullptr, "null argument");
+  if (!strcmp(key, "grid_mult"))
+    s->opt_grid_mult = (int)value;
+  else if (!strcmp(key, "restart_variant"))
+    s->opt_restart_variant = (int)value;
+  else if (!strcmp(key, "ortho_variant"))
+    s->opt_ortho_variant = (int)value;
+  else if (!strcmp(key, "spmv_tile"))
+    s->opt_spmv_tile = (int)value;
+  else
+    return set_err(AB200_EINVAL, "unknown option '%s'", key);
+  return AB200_OK;
+}
+
+int ab200_host_alloc(void** out, int64_t bytes) {
+  REQUIRE(out != nullptr && bytes > 0, "bad argument");
+  CU(cudaMallocHost(out, (size_t)bytes));
+  return AB200_OK;
+}
+int ab200_host_free(void* p) {
+  if (p) CU(cudaFreeHost(p));
+  return AB200_OK;
+}
+
+}  // extern "C"

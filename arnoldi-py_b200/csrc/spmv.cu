@@ -1,0 +1,223 @@
+// spmv.cu -- CSR sparse matrix x complex128 vector  (the reference's `A @ V[:, j]`,
+// decomposition.py:57-58, which lands in scipy's csr_matvec).
+//
+// Work decomposition ("nnz tiles with row-aligned edges"):
+//   * the nnz range is cut into tiles of `tile` entries; tile b starts at the first
+//     row whose indptr >= b * tile (rowblk[], built once per matrix on the device),
+//     so every block owns whole rows and about the same number of non-zeros no
+//     matter how skewed the row lengths are (the merge-path idea, with the split
+//     snapped to row boundaries);
+//   * a block stages its tile of values + column ids into shared memory with
+//     coalesced 128-bit loads, then one thread per row walks its segment in STORED
+//     ORDER with separate multiply and add -- the same operation order as scipy's
+//     csr_matvec, so for rows handled this way y is bit-identical to scipy;
+//   * a row whose part of the tile is long (>= kLongRow entries) is summed by the
+//     whole block instead (fixed-order tree), and a row longer than a tile is carried
+//     across the block's tile iterations through y.
+// x is gathered with 128-bit read-only loads; for banded matrices consecutive rows
+// gather consecutive x entries, so the gathers coalesce and hit L2.
+#include "kernels.cuh"
+
+namespace ab200 {
+
+constexpr int kSpmvThreads = 256;
+constexpr int kLongRow = 96;
+constexpr int kMaxLongPerTile = 64;
+
+template <typename T>
+struct ValOps;
+template <>
+struct ValOps<double> {
+  // (a + 0i) * x, rounded like numpy/scipy's complex multiply with a zero imaginary part
+  static __device__ __forceinline__ cplx mul(double a, cplx x) {
+    return make_double2(__dmul_rn(a, x.x), __dmul_rn(a, x.y));
+  }
+};
+template <>
+struct ValOps<cplx> {
+  // (ar*xr - ai*xi) + i (ar*xi + ai*xr), each product and sum rounded separately (no FMA)
+  static __device__ __forceinline__ cplx mul(cplx a, cplx x) {
+    return make_double2(__dsub_rn(__dmul_rn(a.x, x.x), __dmul_rn(a.y, x.y)),
+                        __dadd_rn(__dmul_rn(a.x, x.y), __dmul_rn(a.y, x.x)));
+  }
+};
+__device__ __forceinline__ cplx cadd_rn(cplx a, cplx b) {
+  return make_double2(__dadd_rn(a.x, b.x), __dadd_rn(a.y, b.y));
+}
+
+template <typename IdxT>
+__global__ void spmv_plan_kernel(const IdxT* __restrict__ indptr, int64_t n, int64_t nnz, int tile,
+                                 int nblocks, int64_t* __restrict__ rowblk) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > nblocks) return;
+  if (b == nblocks) {
+    rowblk[b] = n;
+    return;
+  }
+  const int64_t target = (int64_t)b * tile;
+  // lower_bound over indptr[0..n]: first row r with indptr[r] >= target
+  int64_t lo = 0, hi = n;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if ((int64_t)indptr[mid] < target)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  rowblk[b] = lo;
+}
+
+template <typename IdxT, typename ValT>
+__global__ void __launch_bounds__(kSpmvThreads) spmv_tile_kernel(SpmvArgs a) {
+  if (a.ctl != nullptr && a.ctl->stop) return;
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ValT* sval = reinterpret_cast<ValT*>(smem_raw);
+  int32_t* scol = reinterpret_cast<int32_t*>(smem_raw + (size_t)(a.tile + 4) * sizeof(ValT));
+  __shared__ int s_nlong;
+  __shared__ int64_t s_long_row[kMaxLongPerTile];
+  __shared__ cplx s_red[kSpmvThreads / kWarp];
+
+  const IdxT* __restrict__ indptr = static_cast<const IdxT*>(a.indptr);
+  const ValT* __restrict__ values = static_cast<const ValT*>(a.values);
+  const int32_t* __restrict__ indices = a.indices;
+  const cplx* __restrict__ x = a.x;
+  const cplx* __restrict__ ghost = a.ghost;
+  const int64_t nloc = a.n_local_cols;
+  const double xs = a.xscale ? *a.xscale : 1.0;
+  const int tid = threadIdx.x;
+  const int tile = a.tile;
+
+  for (int b = blockIdx.x; b < a.nblocks; b += gridDim.x) {
+    const int64_t r0 = a.rowblk[b], r1 = a.rowblk[b + 1];
+    if (r0 >= r1) continue;
+    const int64_t s = (int64_t)indptr[r0], e = (int64_t)indptr[r1];
+    // at least one iteration so that empty rows get y = 0
+    for (int64_t cs = s; cs == s || cs < e; cs += tile) {
+      const int64_t ce = (cs + tile < e) ? cs + tile : e;
+      const int cnt = (int)(ce - cs);
+      // stage from the 4-entry-aligned address at or below cs so the 128-bit path always applies;
+      // the (at most 3) leading entries belong to the previous tile and are never read back
+      const int off = (int)(cs & 3);
+      const int64_t ca = cs - off;
+      const int tot = cnt + off;
+      __syncthreads();  // previous iteration's readers are done with smem
+      if (tid == 0) s_nlong = 0;
+      {
+        const int nvec = tot >> 2;
+        const int4* c4 = reinterpret_cast<const int4*>(indices + ca);
+        for (int k = tid; k < nvec; k += kSpmvThreads) reinterpret_cast<int4*>(scol)[k] = __ldg(c4 + k);
+        for (int k = (nvec << 2) + tid; k < tot; k += kSpmvThreads) scol[k] = indices[ca + k];
+        const double2* v2 = reinterpret_cast<const double2*>(values + ca);
+        if (sizeof(ValT) == 8) {
+          for (int k = tid; k < (tot >> 1); k += kSpmvThreads)
+            reinterpret_cast<double2*>(sval)[k] = ld_stream(v2 + k);
+          if ((tot & 1) && tid == 0) sval[tot - 1] = values[ca + tot - 1];
+        } else {
+          for (int k = tid; k < tot; k += kSpmvThreads)
+            reinterpret_cast<double2*>(sval)[k] = ld_stream(v2 + k);
+        }
+      }
+      __syncthreads();
+      // ---- one thread per row, stored order
+      for (int64_t row = r0 + tid; row < r1; row += kSpmvThreads) {
+        const int64_t rs = (int64_t)indptr[row], re = (int64_t)indptr[row + 1];
+        if (re <= cs && !(rs == re && cs == s)) continue;  // finished in an earlier tile
+        if (rs >= ce && rs != re) continue;                // starts in a later tile
+        const int64_t lo = rs > cs ? rs : cs;
+        const int64_t hi = re < ce ? re : ce;
+        const int len = (int)(hi - lo);
+        if (len >= kLongRow) {
+          const int slot = atomicAdd(&s_nlong, 1);
+          if (slot < kMaxLongPerTile) {
+            s_long_row[slot] = row;
+            continue;
+          }
+        }
+        cplx acc = (rs < cs) ? a.y[row] : make_double2(0.0, 0.0);
+        int k = (int)(lo - ca);
+        const int kend = (int)(hi - ca);
+        for (; k + 4 <= kend; k += 4) {
+          cplx xv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int64_t col = scol[k + u];
+            xv[u] = (col < nloc) ? ld_ro(x + col) : ld_ro(ghost + (col - nloc));
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) acc = cadd_rn(acc, ValOps<ValT>::mul(sval[k + u], xv[u]));
+        }
+        for (; k < kend; ++k) {
+          const int64_t col = scol[k];
+          const cplx xv = (col < nloc) ? ld_ro(x + col) : ld_ro(ghost + (col - nloc));
+          acc = cadd_rn(acc, ValOps<ValT>::mul(sval[k], xv));
+        }
+        if (re <= ce) acc = cscale(acc, xs);  // row complete: apply the lazy scale of x
+        a.y[row] = acc;
+      }
+      __syncthreads();
+      // ---- long rows: the whole block reduces one row segment at a time
+      const int nlong = s_nlong < kMaxLongPerTile ? s_nlong : kMaxLongPerTile;
+      for (int l = 0; l < nlong; ++l) {
+        const int64_t row = s_long_row[l];
+        const int64_t rs = (int64_t)indptr[row], re = (int64_t)indptr[row + 1];
+        const int64_t lo = rs > cs ? rs : cs;
+        const int64_t hi = re < ce ? re : ce;
+        cplx acc = make_double2(0.0, 0.0);
+        for (int k = (int)(lo - ca) + tid; k < (int)(hi - ca); k += kSpmvThreads) {
+          const int64_t col = scol[k];
+          const cplx xv = (col < nloc) ? ld_ro(x + col) : ld_ro(ghost + (col - nloc));
+          acc = cadd_rn(acc, ValOps<ValT>::mul(sval[k], xv));
+        }
+        acc = warp_sum(acc);
+        if ((tid & 31) == 0) s_red[tid >> 5] = acc;
+        __syncthreads();
+        if (tid == 0) {
+          cplx t = (rs < cs) ? a.y[row] : make_double2(0.0, 0.0);
+          for (int k = 0; k < kSpmvThreads / kWarp; ++k) t = cadd_rn(t, s_red[k]);
+          if (re <= ce) t = cscale(t, xs);
+          a.y[row] = t;
+        }
+        __syncthreads();
+      }
+    }
+  }
+}
+
+cudaError_t launch_spmv_plan(const void* indptr, int indptr_bits, int64_t n, int64_t nnz, int tile,
+                             int nblocks, int64_t* rowblk, cudaStream_t st) {
+  const int threads = 256;
+  const int grid = (nblocks + 1 + threads - 1) / threads;
+  if (indptr_bits == 32)
+    spmv_plan_kernel<int32_t><<<grid, threads, 0, st>>>(static_cast<const int32_t*>(indptr), n, nnz,
+                                                        tile, nblocks, rowblk);
+  else
+    spmv_plan_kernel<int64_t><<<grid, threads, 0, st>>>(static_cast<const int64_t*>(indptr), n, nnz,
+                                                        tile, nblocks, rowblk);
+  return cudaGetLastError();
+}
+
+template <typename IdxT, typename ValT>
+static cudaError_t launch_spmv_t(const SpmvArgs& a, cudaStream_t st) {
+  const size_t smem = (size_t)(a.tile + 4) * (sizeof(ValT) + sizeof(int32_t));
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(spmv_tile_kernel<IdxT, ValT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         96 * 1024);
+    attr_done = true;
+  }
+  const int grid = a.nblocks;  // one tile per block; blocks are small and many per SM
+  spmv_tile_kernel<IdxT, ValT><<<grid, kSpmvThreads, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_spmv(const SpmvArgs& a, int indptr_bits, int value_kind, cudaStream_t st) {
+  if (indptr_bits == 32) {
+    return value_kind == 0 ? launch_spmv_t<int32_t, double>(a, st)
+                           : launch_spmv_t<int32_t, cplx>(a, st);
+  }
+  return value_kind == 0 ? launch_spmv_t<int64_t, double>(a, st)
+                         : launch_spmv_t<int64_t, cplx>(a, st);
+}
+
+}  // namespace ab200

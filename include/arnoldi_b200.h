@@ -1,0 +1,146 @@
+/*
+ * arnoldi_b200.h -- C ABI of the B200-native Krylov-Schur hot path.
+ *
+ * Drop-in boundary for cournape/arnoldi-py's partial_schur().  The reference is
+ * pure Python and has no FFI of its own; each entry point
+ * below replaces one n-length call site of the reference, cited as file:line
+ * under /root/reference/src/arnoldi.  Everything n-length runs as sm_100a CUDA
+ * and stays in HBM; the (max_dim+1) x max_dim projected matrix H, the Schur
+ * reorder, convergence tests and sort_function stay on the host
+ * (krylov_schur.py:69-76,83-101).
+ *
+ * Conventions
+ *   - plain C types only; complex128 is passed as interleaved (re, im) doubles.
+ *   - every function returns 0 on success, a negative AB200_E* code otherwise;
+ *     ab200_last_error() gives the message for the calling thread.
+ *   - one handle = one GPU = one block of rows [row0, row0 + nrows_local) of A
+ *     and of the Krylov basis V.  A single-GPU solve has row0 = 0,
+ *     nrows_local = n_global.
+ *   - a handle is used from one host thread at a time (krylov_schur.py is
+ *     single-threaded); different handles may be used concurrently.
+ *   - there is no CPU fallback: without a CUDA device every call fails.
+ */
+#ifndef ARNOLDI_B200_H
+#define ARNOLDI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AB200_ABI_VERSION 1
+
+#define AB200_OK 0
+#define AB200_EINVAL (-1)  /* bad argument (maps to AssertionError in Python) */
+#define AB200_ECUDA (-2)   /* CUDA runtime / kernel failure                   */
+#define AB200_ENOMEM (-3)  /* device or pinned allocation failed              */
+#define AB200_ESTATE (-4)  /* call order violated (e.g. expand before set_csr) */
+#define AB200_ECOMM (-5)   /* multi-GPU communicator failure                  */
+
+/* value_kind of the CSR values array */
+#define AB200_F64 0   /* float64 values (mark, Laplacians: matrices.py:73) */
+#define AB200_C128 1  /* complex128 values (scripts/benchmark-partial-schur.py:78) */
+
+/* ortho_kind: the orthonormalisation plug (ortho.py) */
+#define AB200_ORTHO_CGS2 0 /* dgks_gs,  ortho.py:56-107 (the reference default, decomposition.py:60) */
+#define AB200_ORTHO_MGS 1  /* dgks_mgs, ortho.py:9-53 */
+
+/* spmv_algo for ab200_set_csr */
+#define AB200_SPMV_AUTO 0
+#define AB200_SPMV_VECTOR 1 /* sub-warp (1..32 lanes) per row              */
+#define AB200_SPMV_STREAM 2 /* row blocks staged through shared memory     */
+#define AB200_SPMV_MERGE 3  /* merge-path split of rows+nnz for skewed rows */
+
+typedef struct ab200_solver ab200_solver; /* opaque */
+
+/* Per-kernel-class accounting since the last ab200_reset_stats(): device time
+ * (CUDA events on the solver's stream, only when timing is enabled), launches,
+ * and ALGORITHMIC bytes (SURVEY.md section 8d formulas, evaluated with the
+ * column counts and DGKS rounds actually executed). */
+typedef struct ab200_stats {
+  double spmv_ms, ortho_pass1_ms, ortho_pass2_ms, mgs_ms, restart_ms;
+  double spmv_bytes, ortho_pass1_bytes, ortho_pass2_bytes, mgs_bytes, restart_bytes;
+  int64_t spmv_launches, ortho_pass1_launches, ortho_pass2_launches, mgs_launches,
+      restart_launches;
+  int64_t arnoldi_steps;   /* true operator applications (matvecs)          */
+  int64_t ortho_rounds;    /* CGS/MGS rounds executed (1 or 2 per step)     */
+  int64_t second_rounds;   /* steps where the DGKS test fired               */
+  int64_t kernel_launches; /* every kernel this library launched            */
+} ab200_stats;
+
+int ab200_abi_version(void);
+const char *ab200_last_error(void);
+/* number of visible CUDA devices, or a negative error code */
+int ab200_device_count(void);
+
+/* Allocate the solver state on `device`: V (nrows_local x (max_dim+1),
+ * complex128, column-major, zero-filled -- krylov_schur.py:42), two n-length
+ * work vectors, the device copy of H and reduction scratch.
+ * Replaces the allocations at krylov_schur.py:42-43. */
+int ab200_create(ab200_solver **out, int device, int64_t n_global, int64_t row0,
+                 int64_t nrows_local, int max_dim);
+int ab200_destroy(ab200_solver *s);
+
+/* Upload this GPU's block of rows of A in CSR form (what scipy holds for
+ * `A @ x`, decomposition.py:58).  indptr has nrows_local+1 entries of
+ * indptr_bits (32 or 64) and is relative to the block (indptr[0] == 0);
+ * indices are GLOBAL column ids (int32, as scipy stores them below 2^31 nnz);
+ * values are float64 or complex128 according to value_kind. */
+int ab200_set_csr(ab200_solver *s, const void *indptr, int indptr_bits, const int32_t *indices,
+                  const void *values, int value_kind, int64_t nnz, int spmv_algo);
+
+/* Copy host complex128 columns into / out of V (column-major, leading dimension
+ * ld_host in elements).  set_columns replaces `V[:, 0] = v0` (krylov_schur.py:46);
+ * get_columns replaces the final `V[:, :nev]` view (krylov_schur.py:110). */
+int ab200_set_columns(ab200_solver *s, int col0, int ncols, const double *host, int64_t ld_host);
+int ab200_get_columns(ab200_solver *s, int col0, int ncols, double *host, int64_t ld_host);
+
+/* Arnoldi expansion from column start_dim to end_dim on the device
+ * (arnoldi_decomposition, decomposition.py:13-68): for each j the SpMV
+ * (decomposition.py:57-58), the orthogonalisation against V[:, :j+1]
+ * (decomposition.py:60 -> ortho.py), the breakdown test (decomposition.py:61-63)
+ * and the normalisation (decomposition.py:65-66).  No host round trip inside.
+ *
+ * h_cols (host, complex128, column-major with leading dimension max_dim+1)
+ * receives, for every executed column j in [start_dim, *n_iter), rows 0..j
+ * (the projections) and, unless step j broke down, row j+1 (beta).
+ * *n_iter is end_dim, or j+1 if step j broke down (beta < tol), in which
+ * case *breakdown = 1 and V[:, j+1] is left un-normalised as in the reference. */
+int ab200_expand(ab200_solver *s, int start_dim, int end_dim, double tol, double eta,
+                 int ortho_kind, double *h_cols, int *n_iter, int *breakdown);
+
+/* Krylov-Schur truncation (krylov_schur.py:78 and :81 in one pass):
+ * V[:, :p] = V[:, :m] Q[:, :p];  V[:, p] = V[:, m].
+ * q is host complex128, column-major m x p with leading dimension ldq. */
+int ab200_restart(ab200_solver *s, const double *q, int64_t ldq, int m, int p);
+
+/* ---- single-operation entry points (the plugs the reference exposes) ---- */
+
+/* y = A x with host vectors (the duck-typed `A @ x`, decomposition.py:58).
+ * x has n_global entries (single GPU) -- complex128. */
+int ab200_spmv(ab200_solver *s, const double *x_host, double *y_host);
+
+/* dgks_gs / dgks_mgs (ortho.py:56,9): orthogonalise host vector w (nrows_local
+ * complex128, updated in place) against V[:, :ncols] currently on the device;
+ * h (ncols complex128) receives the projections. */
+int ab200_ortho(ab200_solver *s, int ncols, double *w_host, double *h_host, double tol,
+                double eta, int ortho_kind, double *beta, int *breakdown);
+
+/* ---- measurement ---- */
+int ab200_set_timing(ab200_solver *s, int enabled); /* CUDA-event timing per kernel class */
+int ab200_reset_stats(ab200_solver *s);
+int ab200_get_stats(ab200_solver *s, ab200_stats *out);
+int ab200_synchronize(ab200_solver *s);
+/* Select kernel variants (for A/B measurements): key is one of "spmv_lanes",
+ * "ortho_variant", "restart_variant", "grid_mult"; value 0 = automatic. */
+int ab200_set_option(ab200_solver *s, const char *key, int64_t value);
+
+/* Pinned host memory for callers that want asynchronous, full-speed uploads. */
+int ab200_host_alloc(void **out, int64_t bytes);
+int ab200_host_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARNOLDI_B200_H */

@@ -18,16 +18,22 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on a B200)")
 
 
-def pytest_collection_modifyitems(config, items):
-    """GPU tests must never be silently skipped on a GPU box: they are only
-    deselected by ``-m "not gpu"``.  Without a device they fail loudly."""
-
-
 @pytest.fixture(scope="session")
 def golden():
     def load(name):
         return np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
     return load
+
+
+@pytest.fixture(scope="session")
+def gpu():
+    """GPU tests never skip silently: without the library or a device they FAIL."""
+    from arnoldi_b200 import _lib
+    lib = _lib.load()
+    n = lib.ab200_device_count()
+    if n < 1:
+        pytest.fail("no CUDA device visible: " + lib.ab200_last_error().decode(), pytrace=False)
+    return lib
 
 
 def csr_from_golden(g, prefix):
@@ -38,6 +44,7 @@ def csr_from_golden(g, prefix):
 
 
 def lap2d(N):
+    """kron form used when the goldens were generated: CSR WITH explicit zeros."""
     import scipy.sparse as sp
     T = sp.diags_array([-np.ones(N - 1), 2 * np.ones(N), -np.ones(N - 1)], offsets=[-1, 0, 1])
     I = sp.eye_array(N)

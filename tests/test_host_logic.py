@@ -1,0 +1,120 @@
+"""CPU-side checks: the C ABI library loads and exports what the header declares,
+the host control logic matches the reference goldens, the fixtures are bit-exact."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import ROOT, csr_from_golden, lap2d
+
+
+def test_library_exports_every_declared_symbol():
+    from arnoldi_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "arnoldi_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(ab200_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no prototypes found in the header"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(raw, name), f"{name} declared in the header but not exported"
+    lib = _lib.load()
+    assert lib.ab200_abi_version() == _lib.ABI_VERSION
+
+
+def test_no_cpu_fallback_without_device():
+    """Without a CUDA device the product path must fail loudly, not fall back."""
+    from arnoldi_b200 import _lib, partial_schur
+    from arnoldi_b200.matrices import mark
+    lib = _lib.load()
+    if lib.ab200_device_count() >= 1:
+        pytest.skip("a GPU is visible here")
+    with pytest.raises(_lib.DeviceError):
+        partial_schur(mark(10), 3, max_dim=5)
+
+
+def test_mark_is_bit_identical_to_reference(golden):
+    from arnoldi_b200.matrices import mark
+    g = golden("matrices")
+    for m in (2, 3, 10, 17, 20, 50):
+        A = mark(m)
+        assert A.shape == tuple(g[f"mark{m}_shape"])
+        np.testing.assert_array_equal(A.indptr, g[f"mark{m}_indptr"])
+        np.testing.assert_array_equal(A.indices, g[f"mark{m}_indices"])
+        np.testing.assert_array_equal(A.data, g[f"mark{m}_data"])  # bit-exact
+    # tests/test_matrices.py:8-19 of the reference
+    np.testing.assert_array_equal(mark(2).toarray(), [[0, 1, 1], [0.5, 0, 0], [0.5, 0, 0]])
+    assert mark(50).shape == (1275, 1275) and mark(50).nnz == 4900
+
+
+def test_laplace_fixtures(golden):
+    from arnoldi_b200.matrices import laplace, laplace_eigen, lap2d as lap2d_direct
+    g = golden("matrices")
+    np.testing.assert_array_equal(laplace(5).toarray(), csr_from_golden(g, "laplace5").toarray())
+    np.testing.assert_array_equal(laplace_eigen(5), g["laplace_eigen5"])
+    for N in (2, 3, 8, 33):
+        A, B = lap2d_direct(N), lap2d(N)
+        B.eliminate_zeros()
+        B.sort_indices()
+        np.testing.assert_array_equal(A.indptr, B.indptr)
+        np.testing.assert_array_equal(A.indices, B.indices)
+        np.testing.assert_array_equal(A.data, B.data)
+    A = lap2d_direct(64)
+    assert A.nnz == 5 * 64 * 64 - 4 * 64 and A.indices.dtype == np.int32
+
+
+def test_ordered_schur_matches_reference(golden):
+    from scipy.linalg import schur
+    from arnoldi_b200.utils import arg_largest_real, ordered_schur
+    g = golden("restart")
+    T1, Q1 = schur(g["Hm"], output="complex")
+    T2, Q2 = ordered_schur(T1, output="complex", sort_function=arg_largest_real)
+    np.testing.assert_allclose(T2, g["T2"], rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(Q2, g["Q2"], rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(Q1 @ Q2, g["Q"], rtol=1e-12, atol=1e-13)
+    with pytest.raises(ValueError):
+        ordered_schur(T1, output="real")
+    # complex64 path (tests/test_utils.py:23-35 of the reference)
+    rng = np.random.default_rng(0)
+    a = (rng.standard_normal((6, 6)) + 1j * rng.standard_normal((6, 6))).astype(np.complex64)
+    T, Z = ordered_schur(a, output="complex")
+    d = np.abs(np.diag(T))
+    assert np.all(d[:-1] >= d[1:] - 1e-6)
+    np.testing.assert_allclose(Z @ T @ Z.conj().T, a, atol=1e-4)
+
+
+def test_operator_conversion():
+    from arnoldi_b200.operator import as_csr
+    A = sp.random(20, 20, density=0.2, random_state=1, format="csr")
+    ip, ix, d, shape = as_csr(A)
+    assert ip is A.indptr and ix is A.indices and d is A.data and shape == (20, 20)
+    ip, ix, d, _ = as_csr(A.tocoo())
+    np.testing.assert_array_equal(d, A.tocoo().tocsr().data)
+    D = A.toarray()
+    ip, ix, d, _ = as_csr(D)
+    np.testing.assert_array_equal(sp.csr_matrix((d, ix, ip), shape=(20, 20)).toarray(), D)
+    ip, ix, d, _ = as_csr(A.astype(np.float32))
+    assert d.dtype == np.float64
+    from scipy.sparse.linalg import aslinearoperator
+    with pytest.raises(TypeError, match="LinearOperator"):
+        as_csr(aslinearoperator(A))
+
+
+def test_history_and_argument_checks():
+    from arnoldi_b200 import History, partial_schur
+    from arnoldi_b200.matrices import mark
+    h = History.from_k(4)
+    assert h.k == 4 and h.matvecs.dtype == np.int32 and h.total_matvecs == 0
+    A = mark(10)
+    # krylov_schur.py:24,27,36: argument errors are AssertionErrors, raised before any device work
+    with pytest.raises(AssertionError):
+        partial_schur(A, 3, max_restarts=0)
+    with pytest.raises(AssertionError):
+        partial_schur(A, 3, max_dim=3)
+    with pytest.raises(AssertionError):
+        partial_schur(A[:, :10], 3)
+    with pytest.raises(AssertionError):
+        partial_schur(A, 3, ortho="householder")
