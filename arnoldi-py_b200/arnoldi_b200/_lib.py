@@ -61,6 +61,8 @@ SIGNATURES = {
     "ab200_reset_stats": (C.c_int, [_P]),
     "ab200_get_stats": (C.c_int, [_P, C.POINTER(Stats)]),
     "ab200_synchronize": (C.c_int, [_P]),
+    "ab200_timer_start": (C.c_int, [_P]),
+    "ab200_timer_stop": (C.c_int, [_P, _D]),
     "ab200_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
     "ab200_host_alloc": (C.c_int, [C.POINTER(_P), C.c_int64]),
     "ab200_host_free": (C.c_int, [_P]),

@@ -130,5 +130,13 @@ class DeviceSolver:
     def synchronize(self):
         _lib.check(self.lib.ab200_synchronize(self._h))
 
+    def timer_start(self):
+        _lib.check(self.lib.ab200_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_double(0.0)
+        _lib.check(self.lib.ab200_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
     def set_option(self, key, value):
         _lib.check(self.lib.ab200_set_option(self._h, key.encode(), int(value)))

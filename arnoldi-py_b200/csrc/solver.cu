@@ -104,7 +104,7 @@ struct ab200_solver {
   std::vector<TimedLaunch> pending;
   std::vector<cudaEvent_t> pool;
   ab200_stats st;
-  bool has_basis_data = false;
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
 };
 
 static cudaEvent_t get_event(ab200_solver* s) {
@@ -277,6 +277,7 @@ int ab200_destroy(ab200_solver* s) {
   if (s->stream) cudaStreamSynchronize(s->stream);
   resolve_pending(s, nullptr);
   for (auto e : s->pool) cudaEventDestroy(e);
+  if (s->t0) cudaEventDestroy(s->t0), cudaEventDestroy(s->t1);
   cudaFree(s->V), cudaFree(s->wtmp), cudaFree(s->xtmp), cudaFree(s->scale), cudaFree(s->Hdev);
   cudaFree(s->hscratch), cudaFree(s->coef), cudaFree(s->part), cudaFree(s->npart);
   cudaFree(s->ticket), cudaFree(s->ctl), cudaFree(s->step_round2), cudaFree(s->qdev);
@@ -649,6 +650,28 @@ int ab200_synchronize(ab200_solver* s) {
   REQUIRE(s != nullptr, "solver is null");
   CU(cudaSetDevice(s->device));
   CU(cudaStreamSynchronize(s->stream));
+  return AB200_OK;
+}
+
+int ab200_timer_start(ab200_solver* s) {
+  REQUIRE(s != nullptr, "solver is null");
+  CU(cudaSetDevice(s->device));
+  if (!s->t0) {
+    CU(cudaEventCreate(&s->t0));
+    CU(cudaEventCreate(&s->t1));
+  }
+  CU(cudaEventRecord(s->t0, s->stream));
+  return AB200_OK;
+}
+int ab200_timer_stop(ab200_solver* s, double* elapsed_ms) {
+  REQUIRE(s != nullptr && elapsed_ms != nullptr, "null argument");
+  if (!s->t0) return set_err(AB200_ESTATE, "ab200_timer_stop without ab200_timer_start");
+  CU(cudaSetDevice(s->device));
+  CU(cudaEventRecord(s->t1, s->stream));
+  CU(cudaEventSynchronize(s->t1));
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, s->t0, s->t1));
+  *elapsed_ms = ms;
   return AB200_OK;
 }
 

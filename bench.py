@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""Benchmark of the partial_schur hot path (BASELINE.json metric) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Workload (``config.workload``): BASELINE config 2 -- 2-D 5-point Laplacian, N = 4096
+(n = 16 777 216 rows, 83 869 696 entries, float64), K = 10, max_dim = 40 (p = 15),
+sort = largest real part, tol = 1e-8, v0 = ``np.random.seed(0); randn(n)`` normalised.
+
+A *step* is one Krylov-Schur restart cycle of that solve at full size: host Schur +
+reorder of H (40 x 40), the in-place truncation V[:, :15] = V Q, and the Arnoldi
+expansion from column 15 to 40 (25 SpMV + 25 CGS2/DGKS orthogonalisations).  The full
+solve needs on the order of 10^3 such cycles at this size, far
+beyond a benchmark run and far beyond what the CPU reference can finish, so the
+headline is the cycle throughput in Arnoldi matvecs per second:
+
+  value  device-timed (CUDA events on the solver's stream), A and V resident in HBM
+  e2e    the public ``partial_schur(A_host, ...)`` call with a bounded number of restarts:
+         CSR + v0 uploaded from pinned host memory and Q, T read back inside the timing
+  roofline       the kernel class with the largest share of the step, algorithmic bytes
+                  / CUDA-event time, against MEASURED_PEAKS.json
+  cpu_baseline   the oracle (a restatement of the reference calling the same SciPy /
+                 OpenBLAS routines) on the host cores, same operator family at reduced n
+
+``--impl reference`` times that CPU path alone, in the same unit.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "arnoldi-py_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+NEV, MAX_DIM, TOL = 10, 40, 1e-8
+P = min(NEV + 5, MAX_DIM - 1)
+GRID_FULL = 4096          # config 2
+GRID_CPU = 1024           # CPU sample: same operator family, n = 1 048 576
+METRIC = "partial_schur Arnoldi matvecs/s (restart cycles, config 2)"
+UNIT = "matvec/s"
+
+
+# ----------------------------------------------------------------------------- helpers
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(np.max(mx)) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def host_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        n = max((d.get("num_threads", 1) for d in threadpool_info()), default=1)
+        return int(n)
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def pinned_csr(dev_lib, A):
+    """Copy the CSR arrays into pinned host memory (done once, outside any timing) so
+    the e2e upload is a pinned -> device copy as the contract asks."""
+    import ctypes as C
+
+    import scipy.sparse as sp
+    keep = []
+
+    def pin(a):
+        ptr = C.c_void_p()
+        rc = dev_lib.ab200_host_alloc(C.byref(ptr), int(a.nbytes))
+        if rc != 0:
+            return a
+        buf = (C.c_char * a.nbytes).from_address(ptr.value)
+        out = np.frombuffer(buf, dtype=a.dtype, count=a.size)
+        out[:] = a
+        keep.append(ptr)
+        return out
+
+    M = sp.csr_matrix((pin(A.data), pin(A.indices), pin(A.indptr)), shape=A.shape, copy=False)
+    return M, keep
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_cycles(steps, warmup, grid=GRID_CPU):
+    """Reference CPU path: restart cycles of the same solve on lap2d(grid), timed with
+    perf_counter around each cycle (scripts/utils.py:161-174 of the reference)."""
+    import oracle
+    from arnoldi_b200.matrices import lap2d
+    from scipy.linalg import schur
+
+    A = lap2d(grid)
+    n = A.shape[0]
+    np.random.seed(0)
+    V = np.zeros((n, MAX_DIM + 1), np.complex128, order="F")
+    H = np.zeros((MAX_DIM + 1, MAX_DIM), np.complex128)
+    V[:, 0] = oracle.rand_unit_vector(n, np.complex128)
+    t_first = time.perf_counter()
+    oracle.arnoldi_expand(A, V, H, TOL, start_dim=0, max_dim=MAX_DIM)
+    t_first = time.perf_counter() - t_first
+
+    def cycle():
+        m = MAX_DIM
+        T1, Q1 = schur(H[:m, :m], output="complex")
+        T2, Q2 = oracle.sorted_schur(T1, oracle.arg_largest_real)
+        Q = Q1 @ Q2
+        spike = H[m, :m] @ Q[:, :P]
+        oracle.restart_update(V, Q, m, P)
+        H[:P, :P] = T2[:P, :P]
+        H[P, :P] = spike
+        H[P, P:] = 0
+        oracle.arnoldi_expand(A, V, H, TOL, start_dim=P, max_dim=m)
+
+    for _ in range(warmup):
+        cycle()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cycle()
+    dt = time.perf_counter() - t0
+    return dict(n=n, seconds=dt, matvecs=steps * (MAX_DIM - P), first_expansion_s=t_first)
+
+
+def cpu_baseline_dict(steps, warmup):
+    r = cpu_cycles(steps, warmup)
+    full_n = GRID_FULL * GRID_FULL
+    rate_sample = r["matvecs"] / r["seconds"]
+    value = rate_sample * r["n"] / full_n   # per-matvec cost is linear in n (bandwidth-bound)
+    return {
+        "value": value, "unit": UNIT, "cores": host_threads(), "kind": "port",
+        "sample": (f"{steps} restart cycles ({r['matvecs']} matvecs, {r['seconds']:.1f} s) of the "
+                   f"same solve on lap2d({GRID_CPU}) n={r['n']}; measured {rate_sample:.2f} "
+                   f"matvec/s there, scaled by n_sample/n_full = 1/{full_n // r['n']} to config 2; "
+                   "oracle = restatement of the reference calling the same scipy csr_matvec "
+                   "(1 thread) / OpenBLAS zgemv, zgemm (all threads)"),
+        "os_cpu_count": os.cpu_count(),
+    }
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, args.steps)
+    base = cpu_baseline_dict(steps, max(0, min(args.warmup, 3)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT,
+        "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * (MAX_DIM - P) / base["value"],
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "c128",
+        "data": "synthetic",
+        "config": workload_config(),
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config():
+    return {"workload": f"lap2d({GRID_FULL}) n={GRID_FULL**2} nnz={5*GRID_FULL**2-4*GRID_FULL} "
+                        f"float64 CSR, K={NEV}, max_dim={MAX_DIM}, p={P}, LR, tol={TOL}, seed 0",
+            "step": f"one Krylov-Schur restart cycle: Schur+reorder (host, {MAX_DIM}x{MAX_DIM}), "
+                    f"truncation V[:, :{P}] = V Q, expansion {P}->{MAX_DIM} "
+                    f"({MAX_DIM-P} SpMV + CGS2/DGKS)",
+            "l2": "inputs larger than L2 (V = 11.0 GB, A = 1.07 GB)"}
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_b200(args):
+    from scipy.linalg import schur
+
+    from arnoldi_b200 import _lib, partial_schur
+    from arnoldi_b200.matrices import lap2d
+    from arnoldi_b200.solver import DeviceSolver
+    from arnoldi_b200.utils import arg_largest_real, ordered_schur, rand_normalized_vector
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        return run_b200_multi(args, rank, world, local)
+
+    lib = _lib.load()
+    if lib.ab200_device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device -- the B200 arm has no CPU fallback")
+    grid = args.grid
+    A = lap2d(grid)
+    n = A.shape[0]
+    np.random.seed(0)
+    v0 = rand_normalized_vector(n, np.complex128)
+    H = np.zeros((MAX_DIM + 1, MAX_DIM), np.complex128)
+
+    dev = DeviceSolver(n, MAX_DIM, device=local)
+    dev.set_timing(True)
+    dev.set_csr(A.indptr, A.indices, A.data)
+    dev.set_columns(0, v0)
+
+    def grow(start):
+        cols, n_iter, brk = dev.expand(start, MAX_DIM, TOL)
+        assert n_iter == MAX_DIM and not brk
+        for j in range(start, n_iter):
+            H[: j + 2, j] = cols[: j + 2, j]
+
+    def cycle():
+        m = MAX_DIM
+        T1, Q1 = schur(H[:m, :m], output="complex")
+        T2, Q2 = ordered_schur(T1, output="complex", sort_function=arg_largest_real)
+        Q = Q1 @ Q2
+        spike = H[m, :m] @ Q[:, :P]
+        dev.restart(Q, m, P)
+        H[:P, :P] = T2[:P, :P]
+        H[P, :P] = spike
+        H[P, P:] = 0
+        grow(P)
+
+    grow(0)
+    for _ in range(max(3, args.warmup)):
+        cycle()
+    dev.synchronize()
+    dev.reset_stats()
+    clocks = ClockSampler(local)
+    clocks.start()
+    dev.timer_start()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cycle()
+    ms = dev.timer_stop()
+    wall = time.perf_counter() - t0
+    clk = clocks.stop()
+    st = dev.stats()
+    matvecs = args.steps * (MAX_DIM - P)
+    assert st["arnoldi_steps"] == matvecs, (st["arnoldi_steps"], matvecs)
+    value = matvecs / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel class (CUDA events inside the timed region)
+    peak, peak_src = measured_peak()
+    classes = {}
+    for key in ("spmv", "ortho_pass1", "ortho_pass2", "restart"):
+        if st[key + "_launches"]:
+            classes[key] = dict(ms=st[key + "_ms"], bytes=st[key + "_bytes"],
+                                launches=st[key + "_launches"],
+                                gbs=st[key + "_bytes"] / st[key + "_ms"] / 1e6)
+    top = max(classes, key=lambda k: classes[k]["ms"])
+    kernels = {k: {"launches": v["launches"], "avg_ms": v["ms"] / v["launches"],
+                   "achieved_gbs": v["gbs"], "frac_of_measured": v["gbs"] / peak,
+                   "frac_of_8tbs": v["gbs"] / 8000.0,
+                   "share_of_step": v["ms"] / ms} for k, v in classes.items()}
+    roofline = {"bound": "hbm", "kernel": top, "achieved": classes[top]["gbs"], "peak": peak,
+                "unit": "GB/s", "frac": classes[top]["gbs"] / peak, "peak_source": peak_src,
+                "traffic": traffic_from_profile(top, grid), "kernels": kernels,
+                "dgks_second_round_fraction": st["second_rounds"] / max(1, st["arnoldi_steps"])}
+    dev.close()
+
+    # ---- e2e through the public API: host CSR -> (Q, T, history) on the host
+    e2e = None
+    if not args.no_e2e:
+        Ap, keep = pinned_csr(lib, A)
+        restarts = args.e2e_restarts
+        out = {}
+        h2d = A.data.nbytes + A.indices.nbytes + A.indptr.nbytes + 16 * n
+        d2h = 16 * n * NEV + 16 * (MAX_DIM + 1) * MAX_DIM
+        times = []
+        for rep in range(args.e2e_reps + 1):
+            np.random.seed(0)
+            stats = {}
+            t0 = time.perf_counter()
+            Q, T, hist = partial_schur(Ap, NEV, max_dim=MAX_DIM, stopping_criterion=TOL,
+                                       sort_function=arg_largest_real, max_restarts=restarts,
+                                       raise_on_no_convergence=False, stats=stats, device=local)
+            dt = time.perf_counter() - t0
+            if rep > 0:
+                times.append(dt)
+            out = stats
+        mv = out["true_matvecs"]
+        e2e = {"value": mv / float(np.mean(times)), "unit": UNIT,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "call": f"partial_schur(A_host, {NEV}, max_dim={MAX_DIM}, max_restarts={restarts}) "
+                       f"= {mv} matvecs per call, {float(np.mean(times)):.3f} s per call incl. "
+                       "v0 = randn(n) on the host, CSR upload from pinned memory, Q/T download",
+               "reps": len(times)}
+        for ptr in keep:
+            lib.ab200_host_free(ptr)
+
+    cpu = None if args.no_cpu else cpu_baseline_dict(args.cpu_steps, 1)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "c128",
+        "data": "synthetic", "config": workload_config() if grid == GRID_FULL else
+        {"workload": f"lap2d({grid}) REDUCED (not config 2)"},
+        "wall_ms_per_step": 1e3 * wall / args.steps,
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+        "gpu_launches": int(st["kernel_launches"]), "clocks": clk,
+    }
+    print(json.dumps(line))
+
+
+def traffic_from_profile(kernel, grid):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture
+    (profiles/traffic.json, written from `ncu --set full`), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        ent = t.get(f"{kernel}@lap2d({grid})")
+        return ent
+    except Exception:
+        return None
+
+
+def run_b200_multi(args, rank, world, local):
+    raise SystemExit("multi-GPU bench not wired yet")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--grid", type=int, default=GRID_FULL, help="lap2d grid side (4096 = config 2)")
+    ap.add_argument("--e2e-restarts", type=int, default=8)
+    ap.add_argument("--e2e-reps", type=int, default=2)
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -132,8 +132,12 @@ int ab200_set_timing(ab200_solver *s, int enabled); /* CUDA-event timing per ker
 int ab200_reset_stats(ab200_solver *s);
 int ab200_get_stats(ab200_solver *s, ab200_stats *out);
 int ab200_synchronize(ab200_solver *s);
+/* Device-side stopwatch on the solver's stream (CUDA events): start, then stop returns
+ * the elapsed milliseconds of everything enqueued in between (after it has finished). */
+int ab200_timer_start(ab200_solver *s);
+int ab200_timer_stop(ab200_solver *s, double *elapsed_ms);
 /* Select kernel variants (for A/B measurements): key is one of "spmv_lanes",
- * "ortho_variant", "restart_variant", "grid_mult"; value 0 = automatic. */
+ * "ortho_variant", "restart_variant", "grid_mult", "spmv_tile"; value 0 = automatic. */
 int ab200_set_option(ab200_solver *s, const char *key, int64_t value);
 
 /* Pinned host memory for callers that want asynchronous, full-speed uploads. */
