@@ -23,11 +23,13 @@ class Stats(C.Structure):
     """Mirror of ``ab200_stats``."""
 
     _fields_ = (
-        [(n, C.c_double) for n in ("spmv_ms", "ortho_pass1_ms", "ortho_pass2_ms", "mgs_ms",
-                                   "restart_ms", "spmv_bytes", "ortho_pass1_bytes",
-                                   "ortho_pass2_bytes", "mgs_bytes", "restart_bytes")]
+        [(n, C.c_double) for n in ("spmv_ms", "ortho_pass1_ms", "ortho_pass2_ms",
+                                   "ortho_fused_ms", "mgs_ms", "restart_ms", "spmv_bytes",
+                                   "ortho_pass1_bytes", "ortho_pass2_bytes", "ortho_fused_bytes",
+                                   "mgs_bytes", "restart_bytes")]
         + [(n, C.c_int64) for n in ("spmv_launches", "ortho_pass1_launches",
-                                    "ortho_pass2_launches", "mgs_launches", "restart_launches",
+                                    "ortho_pass2_launches", "ortho_fused_launches",
+                                    "mgs_launches", "restart_launches",
                                     "arnoldi_steps", "ortho_rounds", "second_rounds",
                                     "kernel_launches")]
     )

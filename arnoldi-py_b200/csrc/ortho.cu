@@ -92,34 +92,46 @@ __device__ void finish_dots(const OrthoArgs& a, int col0, int ncols, double* red
   if (want_norm && tid == 0) a.ctl->nrm0sq = red[2 * ncols];
 }
 
+// End of an Arnoldi step: breakdown test, H[j+1, j], lazy scale of the new column.
+__device__ void finalize_step(const OrthoArgs& a, double beta) {
+  StepCtl* ctl = a.ctl;
+  if (!a.finalize) return;
+  ctl->steps_total += 1;
+  if (beta < a.tol) {  // ortho.py:107, decomposition.py:61-63
+    ctl->stop = 1;
+    ctl->broke_at = a.j;
+    a.scale[a.j + 1] = 1.0;  // the reference leaves w un-normalised
+  } else {
+    a.hcol[a.j + 1] = make_double2(beta, 0.0);  // decomposition.py:65
+    a.scale[a.j + 1] = 1.0 / beta;              // decomposition.py:66, applied lazily
+  }
+}
+
+// DGKS test after the first round (ortho.py:101, strict `<`); records the decision.
+__device__ bool dgks_decide(const OrthoArgs& a, double beta) {
+  StepCtl* ctl = a.ctl;
+  ctl->beta = beta;
+  ctl->rounds_total += 1;
+  const bool again = beta < a.eta * sqrt(ctl->nrm0sq);
+  ctl->round2 = again ? 1 : 0;
+  if (again) ctl->second_total += 1;
+  if (a.step_flag) *a.step_flag = again ? 1 : 0;
+  return again;
+}
+
 // After pass 2 (or the last MGS axpy): beta, DGKS decision, breakdown, H[j+1,j], scale.
 __device__ void finish_norm(const OrthoArgs& a, double nrmsq) {
   StepCtl* ctl = a.ctl;
   const double beta = sqrt(nrmsq);
-  ctl->beta = beta;
   bool again = false;
   if (a.round == 1) {
-    ctl->rounds_total += 1;
-    // ortho.py:101 `beta < eta * beta_before` (strict)
-    again = beta < a.eta * sqrt(ctl->nrm0sq);
-    ctl->round2 = again ? 1 : 0;
-    if (again) ctl->second_total += 1;
-    if (a.step_flag) *a.step_flag = again ? 1 : 0;
+    again = dgks_decide(a, beta);
   } else {
+    ctl->beta = beta;
     ctl->rounds_total += 1;
     ctl->round2 = 0;
   }
-  if (!again && a.finalize) {
-    ctl->steps_total += 1;
-    if (beta < a.tol) {  // ortho.py:107, decomposition.py:61-63
-      ctl->stop = 1;
-      ctl->broke_at = a.j;
-      a.scale[a.j + 1] = 1.0;  // the reference leaves w un-normalised
-    } else {
-      a.hcol[a.j + 1] = make_double2(beta, 0.0);  // decomposition.py:65
-      a.scale[a.j + 1] = 1.0 / beta;              // decomposition.py:66, applied lazily
-    }
-  }
+  if (!again) finalize_step(a, beta);
 }
 
 // ------------------------------------------------------------------ CGS pass 1
@@ -332,6 +344,152 @@ __global__ void __launch_bounds__(256) cgs_pass2_kernel(OrthoArgs a) {
   if (threadIdx.x == 0) finish_norm(a, s_red[0]);
 }
 
+// ------------------------------------------------------------------ CGS fused pass
+// Round-1 pass 2 and round-2 pass 1 in ONE sweep over the basis:
+//     w' = w - U coef          (ortho.py:96)
+//     g' = U^H w', ||w'||^2    (ortho.py:98 and, should the DGKS test fire, :102)
+// Row r of w' depends only on row r of U, so while a chunk of U is in registers it is
+// used twice.  If the DGKS test then fires (100% of the steps on the 2-D Laplacian) the
+// second round only needs its pass 2; if it does not, g' is simply dropped.  Same block
+// shape as pass 1: warp k owns columns [k*CT, k*CT+CT); the per-warp partial sums of
+// U coef meet in shared memory (double buffered: one __syncthreads per chunk).
+template <int CT, int R>
+__global__ void __launch_bounds__(512) cgs_fused_kernel(OrthoArgs a) {
+  StepCtl* ctl = a.ctl;
+  if (ctl->stop) return;
+
+  constexpr int ROWS = kWarp * R;
+  extern __shared__ __align__(16) unsigned char fused_smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nwarps = blockDim.x >> 5;
+  const int c = a.ncols;
+  cplx* spart = reinterpret_cast<cplx*>(fused_smem);  // [2][nwarps][ROWS]
+  cplx* scoef = spart + 2 * nwarps * ROWS;            // [nwarps * CT]
+  for (int i = threadIdx.x; i < nwarps * CT; i += blockDim.x)
+    scoef[i] = i < c ? a.coef[i] : make_double2(0.0, 0.0);
+  __syncthreads();
+
+  const int mycol0 = warp * CT;
+  int mycols = c - mycol0;
+  mycols = mycols < 0 ? 0 : (mycols > CT ? CT : mycols);
+  const int64_t ld = a.ld;
+  cplx* w = a.w;
+  const cplx* __restrict__ U = a.U + (int64_t)mycol0 * ld;
+  cplx cf[CT];
+#pragma unroll
+  for (int k = 0; k < CT; ++k) cf[k] = scoef[mycol0 + k];
+
+  cplx acc[CT];
+#pragma unroll
+  for (int k = 0; k < CT; ++k) acc[k] = make_double2(0.0, 0.0);
+  double nacc = 0.0;
+
+  const int64_t nchunks = (a.n + ROWS - 1) / ROWS;
+  int buf = 0;
+  for (int64_t q = blockIdx.x; q < nchunks; q += gridDim.x, buf ^= 1) {
+    const int64_t base = q * ROWS + lane;
+    const bool full = q * ROWS + ROWS <= a.n;
+    cplx wv[R];
+    cplx v[CT][R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const bool ok = full || base + r * kWarp < a.n;
+      wv[r] = ok ? ld_plain(w + base + r * kWarp) : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int k = 0; k < CT; ++k) {
+      if (k < mycols) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const bool ok = full || base + r * kWarp < a.n;
+          v[k][r] = ok ? ld_stream(U + (int64_t)k * ld + base + r * kWarp) : make_double2(0.0, 0.0);
+        }
+      }
+    }
+    // my columns' share of U coef for these rows
+    cplx* mine = spart + ((size_t)buf * nwarps + warp) * ROWS;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      cplx t = make_double2(0.0, 0.0);
+#pragma unroll
+      for (int k = 0; k < CT; ++k)
+        if (k < mycols) cfma(t, v[k][r], cf[k]);
+      mine[r * kWarp + lane] = t;
+    }
+    __syncthreads();
+    // every warp rebuilds w' for the chunk (same order everywhere: bit-identical copies)
+    const cplx* all = spart + (size_t)buf * nwarps * ROWS;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      cplx t = make_double2(0.0, 0.0);
+      for (int k2 = 0; k2 < nwarps; ++k2) t = cadd(t, all[k2 * ROWS + r * kWarp + lane]);
+      wv[r].x -= t.x;
+      wv[r].y -= t.y;
+    }
+    if (warp == 0) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const bool ok = full || base + r * kWarp < a.n;
+        if (ok) {
+          st_stream(w + base + r * kWarp, wv[r]);
+          nacc = fma(wv[r].x, wv[r].x, nacc);
+          nacc = fma(wv[r].y, wv[r].y, nacc);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < CT; ++k) {
+      if (k < mycols) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) cfma_conj(acc[k], v[k][r], wv[r]);
+      }
+    }
+  }
+
+  const int gcap = a.grid_cap;
+#pragma unroll
+  for (int k = 0; k < CT; ++k) {
+    if (k < mycols) {
+      cplx s = warp_sum(acc[k]);
+      if (lane == 0) a.part[(size_t)(mycol0 + k) * gcap + blockIdx.x] = s;
+    }
+  }
+  if (warp == 0) {
+    double s = warp_sum(nacc);
+    if (lane == 0) a.npart[blockIdx.x] = s;
+  }
+
+  __shared__ int s_last;
+  __shared__ int s_again;
+  if (!last_block_ticket(a.ticket, gridDim.x, &s_last)) return;
+
+  double* red = reinterpret_cast<double*>(fused_smem);  // 2*c + 1 doubles (spart is free now)
+  for (int i = warp; i < c; i += nwarps) {
+    cplx g = sum_partials(a.part + (size_t)i * gcap, gridDim.x, lane);
+    if (lane == 0) {
+      red[2 * i] = g.x;
+      red[2 * i + 1] = g.y;
+    }
+  }
+  if (warp == 0) {
+    double s = sum_partials(a.npart, gridDim.x, lane);
+    if (lane == 0) red[2 * c] = s;
+  }
+  __syncthreads();
+  peer_allreduce(a.comm, red, 2 * c + 1, ctl);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double beta = sqrt(red[2 * c]);
+    const bool again = dgks_decide(a, beta);
+    if (!again) finalize_step(a, beta);
+    s_again = again ? 1 : 0;
+  }
+  __syncthreads();
+  // second round wanted: h += s g', pass-2 coefficients of round 2   (ortho.py:102-103)
+  if (s_again) finish_dots(a, 0, c, red, false);
+}
+
 // ------------------------------------------------------------------ MGS step kernel
 // Kernel i of an MGS sweep (ortho.py:39-41 / :47-50), i = 0..c:
 //   if i > 0:  w -= coef[i-1] * U_{i-1}          (axpy of the previous column)
@@ -477,6 +635,38 @@ cudaError_t launch_cgs_pass1(const OrthoArgs& a, int num_sms, cudaStream_t st, i
     case 6: return launch_pass1_t<6, 2>(a, warps, num_sms, st, grid_mult);
     case 7: return launch_pass1_t<7, 2>(a, warps, num_sms, st, grid_mult);
     default: return launch_pass1_t<8, 2>(a, warps, num_sms, st, grid_mult);
+  }
+}
+
+template <int CT, int R>
+static cudaError_t launch_fused_t(const OrthoArgs& a, int warps, int num_sms, cudaStream_t st,
+                                  int grid_mult) {
+  OrthoArgs args = a;
+  args.accumulate = 1;  // the dots it produces belong to round 2
+  const int threads = warps * kWarp;
+  const int64_t nchunks = (a.n + kWarp * R - 1) / (kWarp * R);
+  int bps = grid_mult > 0 ? grid_mult : (threads <= 128 ? 6 : (threads <= 256 ? 4 : 2));
+  const int grid = pick_grid(nchunks, bps, num_sms, a.grid_cap);
+  size_t smem = sizeof(cplx) * ((size_t)2 * warps * kWarp * R + (size_t)warps * CT);
+  const size_t need = sizeof(double) * (2 * a.ncols + 2);
+  if (smem < need) smem = need;
+  cgs_fused_kernel<CT, R><<<grid, threads, smem, st>>>(args);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_cgs_fused(const OrthoArgs& a, int num_sms, cudaStream_t st, int grid_mult) {
+  int ct, warps;
+  pass1_shape(a.ncols, &ct, &warps);
+  if (warps > 16) return cudaErrorInvalidValue;
+  switch (ct) {
+    case 1: return launch_fused_t<1, 4>(a, warps, num_sms, st, grid_mult);
+    case 2: return launch_fused_t<2, 4>(a, warps, num_sms, st, grid_mult);
+    case 3: return launch_fused_t<3, 4>(a, warps, num_sms, st, grid_mult);
+    case 4: return launch_fused_t<4, 4>(a, warps, num_sms, st, grid_mult);
+    case 5: return launch_fused_t<5, 2>(a, warps, num_sms, st, grid_mult);
+    case 6: return launch_fused_t<6, 2>(a, warps, num_sms, st, grid_mult);
+    case 7: return launch_fused_t<7, 2>(a, warps, num_sms, st, grid_mult);
+    default: return launch_fused_t<8, 2>(a, warps, num_sms, st, grid_mult);
   }
 }
 

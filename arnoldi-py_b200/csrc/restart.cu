@@ -12,19 +12,26 @@
 
 namespace ab200 {
 
-template <int PT>
-__global__ void __launch_bounds__(512) restart_kernel(RestartArgs a, int pw) {
+// coherent 128-bit load whose issue point is pinned (volatile): batches of these are
+// issued back to back so several columns of a row are in flight per thread
+__device__ __forceinline__ cplx ld_pinned(const cplx* p) {
+  cplx r;
+  asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  return r;
+}
+
+template <int PT, bool QS>
+__global__ void __launch_bounds__(512) restart_kernel(RestartArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int m = a.m, p = a.p;
   // coefficients: shared memory when they fit comfortably, else straight from global
   // (uniform addresses: one L1-resident broadcast load per warp)
-  const cplx* sq = a.q;  // [m][p]
-  if (pw > 0) {
-    cplx* s = reinterpret_cast<cplx*>(smem_raw);
-    for (int k = threadIdx.x; k < m * p; k += blockDim.x) s[k] = a.q[k];
+  cplx* sq_s = reinterpret_cast<cplx*>(smem_raw);  // [m][p]
+  if (QS) {
+    for (int k = threadIdx.x; k < m * p; k += blockDim.x) sq_s[k] = a.q[k];
     __syncthreads();
-    sq = s;
   }
+  const cplx* __restrict__ sq_g = a.q;
 
   const int lane = threadIdx.x & 31;
   const int wy = threadIdx.x >> 5;
@@ -33,6 +40,7 @@ __global__ void __launch_bounds__(512) restart_kernel(RestartArgs a, int pw) {
   nk = nk < 0 ? 0 : (nk > PT ? PT : nk);
   const int64_t ld = a.ld;
   const int64_t nchunks = (a.n + kWarp - 1) / kWarp;
+  constexpr int B = 4;  // columns per load batch; two batches are in flight
 
   for (int64_t q = blockIdx.x; q < nchunks; q += gridDim.x) {
     const int64_t row = q * kWarp + lane;
@@ -41,29 +49,30 @@ __global__ void __launch_bounds__(512) restart_kernel(RestartArgs a, int pw) {
     cplx acc[PT];
 #pragma unroll
     for (int k = 0; k < PT; ++k) acc[k] = make_double2(0.0, 0.0);
-    int i = 0;
-    for (; i + 4 <= m; i += 4) {
-      cplx u[4];
+    cplx cur[B], nxt[B];
 #pragma unroll
-      for (int t = 0; t < 4; ++t) u[t] = src[(int64_t)(i + t) * ld];
+    for (int t = 0; t < B; ++t) cur[t] = ld_pinned(src + (int64_t)(t < m ? t : m - 1) * ld);
+    for (int i = 0; i < m; i += B) {
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const cplx* qrow = sq + (i + t) * p + k0;
-#pragma unroll
-        for (int k = 0; k < PT; ++k)
-          if (k < nk) cfma(acc[k], u[t], qrow[k]);
+      for (int t = 0; t < B; ++t) {
+        const int col = i + B + t;
+        nxt[t] = ld_pinned(src + (int64_t)(col < m ? col : m) * ld);  // column m is read anyway
       }
-    }
-    for (; i < m; ++i) {
-      const cplx u = src[(int64_t)i * ld];
-      const cplx* qrow = sq + i * p + k0;
 #pragma unroll
-      for (int k = 0; k < PT; ++k)
-        if (k < nk) cfma(acc[k], u, qrow[k]);
+      for (int t = 0; t < B; ++t) {
+        if (i + t < m) {
+          const int qo = (i + t) * p + k0;
+#pragma unroll
+          for (int k = 0; k < PT; ++k)
+            if (k < nk) cfma(acc[k], cur[t], QS ? sq_s[qo + k] : __ldg(sq_g + qo + k));
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < B; ++t) cur[t] = nxt[t];
     }
     cplx tail = make_double2(0.0, 0.0);
-    if (wy == 0) tail = cscale(src[(int64_t)m * ld], a.scale_m);
-    __syncthreads();  // every warp of the block has read its inputs for these rows
+    if (wy == 0) tail = cscale(ld_pinned(src + (int64_t)m * ld), a.scale_m);
+    if (blockDim.x > kWarp) __syncthreads();  // every warp of the block has read these rows
     if (ok) {
       cplx* dst = a.U + row;
 #pragma unroll
@@ -79,31 +88,32 @@ static cudaError_t launch_restart_t(const RestartArgs& a, int num_sms, cudaStrea
   const int nw = (a.p + PT - 1) / PT;
   const int threads = nw * kWarp;
   size_t smem = sizeof(cplx) * (size_t)a.m * a.p;
-  int pw = 1;  // 1: stage the coefficients in shared memory
-  if (smem > 100 * 1024) {
-    smem = 0;
-    pw = 0;
-  }
+  const bool qs = smem <= 100 * 1024;  // stage the coefficients in shared memory
+  if (!qs) smem = 0;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(restart_kernel<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         200 * 1024);
+    cudaFuncSetAttribute(restart_kernel<PT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         100 * 1024);
     attr_done = true;
   }
   const int64_t nchunks = (a.n + kWarp - 1) / kWarp;
   int bps = 2048 / threads;
-  if (bps > 8) bps = 8;
+  if (bps > 16) bps = 16;
   if (bps < 1) bps = 1;
   int64_t grid = (int64_t)num_sms * bps;
   if (grid > nchunks) grid = nchunks;
   if (grid < 1) grid = 1;
-  restart_kernel<PT><<<(int)grid, threads, smem, st>>>(a, pw);
+  if (qs)
+    restart_kernel<PT, true><<<(int)grid, threads, smem, st>>>(a);
+  else
+    restart_kernel<PT, false><<<(int)grid, threads, smem, st>>>(a);
   return cudaGetLastError();
 }
 
 cudaError_t launch_restart(const RestartArgs& a, int num_sms, cudaStream_t st, int variant) {
   // PT outputs per warp; at most 16 warps per block
-  int pt = variant > 0 ? variant : 8;
+  // default: the fewest warps per row group (p <= 16 needs no block barrier at all)
+  int pt = variant > 0 ? variant : (a.p <= 8 ? 8 : 16);
   while ((a.p + pt - 1) / pt > 16) pt *= 2;
   if (pt <= 4) return launch_restart_t<4>(a, num_sms, st);
   if (pt <= 8) return launch_restart_t<8>(a, num_sms, st);

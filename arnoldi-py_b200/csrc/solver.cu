@@ -42,7 +42,7 @@ static int set_err(int code, const char* fmt, ...) {
   } while (0)
 
 // ---------------------------------------------------------------------------- solver
-enum KClass { K_SPMV = 0, K_PASS1, K_PASS2, K_MGS, K_RESTART, K_OTHER, K_NCLASS };
+enum KClass { K_SPMV = 0, K_PASS1, K_PASS2, K_FUSED, K_MGS, K_RESTART, K_OTHER, K_NCLASS };
 
 struct TimedLaunch {
   int cls;
@@ -169,6 +169,10 @@ static void resolve_pending(ab200_solver* s, const int* step_round2 /* may be nu
         s->st.ortho_pass2_ms += ms, s->st.ortho_pass2_bytes += t.bytes,
             s->st.ortho_pass2_launches++;
         break;
+      case K_FUSED:
+        s->st.ortho_fused_ms += ms, s->st.ortho_fused_bytes += t.bytes,
+            s->st.ortho_fused_launches++;
+        break;
       case K_MGS:
         s->st.mgs_ms += ms, s->st.mgs_bytes += t.bytes, s->st.mgs_launches++;
         break;
@@ -234,6 +238,26 @@ static OrthoArgs make_ortho_args(ab200_solver* s, cplx* w, int ncols, int j, dou
 static int enqueue_ortho(ab200_solver* s, OrthoArgs a, int ortho_kind) {
   const double nb = 16.0 * (double)s->n;
   const int c = a.ncols;
+  if (ortho_kind == AB200_ORTHO_CGS2 && s->opt_ortho_variant == 0) {
+    // default CGS2/DGKS schedule: 3 sweeps when the DGKS test fires, 2 when it does not
+    a.round = 1;
+    a.accumulate = 0;
+    {
+      LaunchScope ls(s, K_PASS1, a.j, 1, nb * (c + 1));
+      CU(launch_cgs_pass1(a, s->num_sms, s->stream, s->opt_grid_mult));
+    }
+    {
+      LaunchScope ls(s, K_FUSED, a.j, 1, nb * (c + 2));
+      CU(launch_cgs_fused(a, s->num_sms, s->stream, s->opt_grid_mult));
+    }
+    a.round = 2;
+    a.accumulate = 1;
+    {
+      LaunchScope ls(s, K_PASS2, a.j, 2, nb * (c + 2));
+      CU(launch_cgs_pass2(a, s->num_sms, s->stream, s->opt_grid_mult));
+    }
+    return AB200_OK;
+  }
   for (int round = 1; round <= 2; ++round) {
     a.round = round;
     a.accumulate = (round == 2);

@@ -299,7 +299,7 @@ def run_b200(args):
     # ---- roofline of the dominant kernel class (CUDA events inside the timed region)
     peak, peak_src = measured_peak()
     classes = {}
-    for key in ("spmv", "ortho_pass1", "ortho_pass2", "restart"):
+    for key in ("spmv", "ortho_pass1", "ortho_fused", "ortho_pass2", "restart"):
         if st[key + "_launches"]:
             classes[key] = dict(ms=st[key + "_ms"], bytes=st[key + "_bytes"],
                                 launches=st[key + "_launches"],

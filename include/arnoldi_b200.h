@@ -59,10 +59,12 @@ typedef struct ab200_solver ab200_solver; /* opaque */
  * and ALGORITHMIC bytes (SURVEY.md section 8d formulas, evaluated with the
  * column counts and DGKS rounds actually executed). */
 typedef struct ab200_stats {
-  double spmv_ms, ortho_pass1_ms, ortho_pass2_ms, mgs_ms, restart_ms;
-  double spmv_bytes, ortho_pass1_bytes, ortho_pass2_bytes, mgs_bytes, restart_bytes;
-  int64_t spmv_launches, ortho_pass1_launches, ortho_pass2_launches, mgs_launches,
-      restart_launches;
+  /* ortho_fused = the sweep that does round-1 pass 2 and round-2 pass 1 together */
+  double spmv_ms, ortho_pass1_ms, ortho_pass2_ms, ortho_fused_ms, mgs_ms, restart_ms;
+  double spmv_bytes, ortho_pass1_bytes, ortho_pass2_bytes, ortho_fused_bytes, mgs_bytes,
+      restart_bytes;
+  int64_t spmv_launches, ortho_pass1_launches, ortho_pass2_launches, ortho_fused_launches,
+      mgs_launches, restart_launches;
   int64_t arnoldi_steps;   /* true operator applications (matvecs)          */
   int64_t ortho_rounds;    /* CGS/MGS rounds executed (1 or 2 per step)     */
   int64_t second_rounds;   /* steps where the DGKS test fired               */
