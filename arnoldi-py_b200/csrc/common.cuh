@@ -36,6 +36,13 @@ __device__ __forceinline__ cplx ld_plain(const cplx* p) {
   asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p) : "memory");
   return r;
 }
+// Coherent 128-bit load the compiler may schedule freely (for data this kernel also writes,
+// at addresses it has not written yet).
+__device__ __forceinline__ cplx ld_coherent(const cplx* p) {
+  cplx r;
+  asm("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  return r;
+}
 __device__ __forceinline__ void st_stream(cplx* p, cplx v) {
   asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y)
                : "memory");

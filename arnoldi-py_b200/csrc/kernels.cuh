@@ -32,7 +32,8 @@ struct OrthoArgs {
 };
 
 cudaError_t launch_cgs_pass1(const OrthoArgs& a, int num_sms, cudaStream_t st, int grid_mult);
-cudaError_t launch_cgs_fused(const OrthoArgs& a, int num_sms, cudaStream_t st, int grid_mult);
+cudaError_t launch_cgs_fused(const OrthoArgs& a, int num_sms, cudaStream_t st, int grid_mult,
+                             int variant, int fused_ct);
 cudaError_t launch_cgs_pass2(const OrthoArgs& a, int num_sms, cudaStream_t st, int grid_mult);
 cudaError_t launch_mgs_step(const OrthoArgs& a, int i, int num_sms, cudaStream_t st,
                             int grid_mult);

@@ -140,7 +140,7 @@ __device__ void finish_norm(const OrthoArgs& a, double nrmsq) {
 // accumulators in registers for the whole kernel.  Lanes run along n, so each
 // load instruction of a warp covers 512 contiguous bytes of one column.
 template <int CT, int R>
-__global__ void __launch_bounds__(512) cgs_pass1_kernel(OrthoArgs a) {
+__global__ void __launch_bounds__(CT < 8 ? 256 : 512) cgs_pass1_kernel(OrthoArgs a) {
   StepCtl* ctl = a.ctl;
   if (ctl->stop) return;
   if (a.round == 2 && !ctl->round2) return;
@@ -353,8 +353,8 @@ __global__ void __launch_bounds__(256) cgs_pass2_kernel(OrthoArgs a) {
 // second round only needs its pass 2; if it does not, g' is simply dropped.  Same block
 // shape as pass 1: warp k owns columns [k*CT, k*CT+CT); the per-warp partial sums of
 // U coef meet in shared memory (double buffered: one __syncthreads per chunk).
-template <int CT, int R>
-__global__ void __launch_bounds__(512) cgs_fused_kernel(OrthoArgs a) {
+template <int CT, int R, bool PF>
+__global__ void __launch_bounds__(CT < 8 && !(CT <= 3 && PF) ? 256 : 512) cgs_fused_kernel(OrthoArgs a) {
   StepCtl* ctl = a.ctl;
   if (ctl->stop) return;
 
@@ -386,16 +386,17 @@ __global__ void __launch_bounds__(512) cgs_fused_kernel(OrthoArgs a) {
   double nacc = 0.0;
 
   const int64_t nchunks = (a.n + ROWS - 1) / ROWS;
-  int buf = 0;
-  for (int64_t q = blockIdx.x; q < nchunks; q += gridDim.x, buf ^= 1) {
+  // software pipeline: the loads of the block's next chunk are issued before the current
+  // chunk is processed, so every warp has requests in flight while it waits at the barrier
+  cplx wv[R], wn[R];
+  cplx v[CT][R], vn[CT][R];
+  auto load_chunk = [&](int64_t q, cplx(&ww)[R], cplx(&vv)[CT][R]) {
     const int64_t base = q * ROWS + lane;
     const bool full = q * ROWS + ROWS <= a.n;
-    cplx wv[R];
-    cplx v[CT][R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const bool ok = full || base + r * kWarp < a.n;
-      wv[r] = ok ? ld_plain(w + base + r * kWarp) : make_double2(0.0, 0.0);
+      ww[r] = ok ? ld_coherent(w + base + r * kWarp) : make_double2(0.0, 0.0);
     }
 #pragma unroll
     for (int k = 0; k < CT; ++k) {
@@ -403,10 +404,19 @@ __global__ void __launch_bounds__(512) cgs_fused_kernel(OrthoArgs a) {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
           const bool ok = full || base + r * kWarp < a.n;
-          v[k][r] = ok ? ld_stream(U + (int64_t)k * ld + base + r * kWarp) : make_double2(0.0, 0.0);
+          vv[k][r] = ok ? ld_stream(U + (int64_t)k * ld + base + r * kWarp) : make_double2(0.0, 0.0);
         }
       }
     }
+  };
+  int buf = 0;
+  if (PF && (int64_t)blockIdx.x < nchunks) load_chunk(blockIdx.x, wv, v);
+  for (int64_t q = blockIdx.x; q < nchunks; q += gridDim.x, buf ^= 1) {
+    const int64_t base = q * ROWS + lane;
+    const bool full = q * ROWS + ROWS <= a.n;
+    const int64_t qn = q + gridDim.x;
+    if (!PF) load_chunk(q, wv, v);
+    if (PF && qn < nchunks) load_chunk(qn, wn, vn);
     // my columns' share of U coef for these rows
     cplx* mine = spart + ((size_t)buf * nwarps + warp) * ROWS;
 #pragma unroll
@@ -444,6 +454,14 @@ __global__ void __launch_bounds__(512) cgs_fused_kernel(OrthoArgs a) {
 #pragma unroll
         for (int r = 0; r < R; ++r) cfma_conj(acc[k], v[k][r], wv[r]);
       }
+    }
+    if (PF && qn < nchunks) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) wv[r] = wn[r];
+#pragma unroll
+      for (int k = 0; k < CT; ++k)
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[k][r] = vn[k][r];
     }
   }
 
@@ -609,15 +627,20 @@ static void pass1_shape(int c, int* ct, int* warps) {
   *warps = w;
 }
 
+template <typename K>
+static int resident_blocks(K kernel, int threads, size_t smem, int* cache);
+
 template <int CT, int R>
 static cudaError_t launch_pass1_t(const OrthoArgs& a, int warps, int num_sms, cudaStream_t st,
                                   int grid_mult) {
   OrthoArgs args = a;
   const int threads = warps * kWarp;
   const int64_t nchunks = (a.n + kWarp * R - 1) / (kWarp * R);
-  int bps = grid_mult > 0 ? grid_mult : (threads <= 128 ? 6 : (threads <= 256 ? 4 : 2));
-  const int grid = pick_grid(nchunks, bps, num_sms, a.grid_cap);
   const size_t smem = sizeof(double) * (2 * a.ncols + 2);
+  static int occ[17] = {0};
+  const int bps = grid_mult > 0 ? grid_mult
+                                : resident_blocks(cgs_pass1_kernel<CT, R>, threads, smem, &occ[warps]);
+  const int grid = pick_grid(nchunks, bps, num_sms, a.grid_cap);
   cgs_pass1_kernel<CT, R><<<grid, threads, smem, st>>>(args);
   return cudaGetLastError();
 }
@@ -638,35 +661,73 @@ cudaError_t launch_cgs_pass1(const OrthoArgs& a, int num_sms, cudaStream_t st, i
   }
 }
 
-template <int CT, int R>
+// resident blocks per SM for a kernel / block shape (cached: the query costs microseconds)
+template <typename K>
+static int resident_blocks(K kernel, int threads, size_t smem, int* cache) {
+  if (*cache == 0) {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, smem) != cudaSuccess ||
+        nb < 1)
+      nb = 1;
+    *cache = nb;
+  }
+  return *cache;
+}
+
+template <int CT, int R, bool PF>
 static cudaError_t launch_fused_t(const OrthoArgs& a, int warps, int num_sms, cudaStream_t st,
                                   int grid_mult) {
   OrthoArgs args = a;
   args.accumulate = 1;  // the dots it produces belong to round 2
   const int threads = warps * kWarp;
   const int64_t nchunks = (a.n + kWarp * R - 1) / (kWarp * R);
-  int bps = grid_mult > 0 ? grid_mult : (threads <= 128 ? 6 : (threads <= 256 ? 4 : 2));
-  const int grid = pick_grid(nchunks, bps, num_sms, a.grid_cap);
   size_t smem = sizeof(cplx) * ((size_t)2 * warps * kWarp * R + (size_t)warps * CT);
   const size_t need = sizeof(double) * (2 * a.ncols + 2);
   if (smem < need) smem = need;
-  cgs_fused_kernel<CT, R><<<grid, threads, smem, st>>>(args);
+  static int occ[17] = {0};
+  const int bps = grid_mult > 0 ? grid_mult
+                                : resident_blocks(cgs_fused_kernel<CT, R, PF>, threads, smem,
+                                                  &occ[warps]);
+  const int grid = pick_grid(nchunks, bps, num_sms, a.grid_cap);
+  cgs_fused_kernel<CT, R, PF><<<grid, threads, smem, st>>>(args);
   return cudaGetLastError();
 }
 
-cudaError_t launch_cgs_fused(const OrthoArgs& a, int num_sms, cudaStream_t st, int grid_mult) {
+// variant: 0 = prefetching, narrow column tiles (<= 3 per warp, up to 16 warps);
+//          2 = no prefetch, pass-1 block shape;  fused_ct > 0 forces the tile width
+cudaError_t launch_cgs_fused(const OrthoArgs& a, int num_sms, cudaStream_t st, int grid_mult,
+                             int variant, int fused_ct) {
   int ct, warps;
-  pass1_shape(a.ncols, &ct, &warps);
-  if (warps > 16) return cudaErrorInvalidValue;
+  const bool pf = (variant != 2);
+  if (fused_ct > 0) {
+    ct = fused_ct > 8 ? 8 : fused_ct;
+    warps = (a.ncols + ct - 1) / ct;
+  } else if (pf) {
+    ct = (a.ncols + 15) / 16;
+    if (ct < 1) ct = 1;
+    // prefer ~2 blocks of <= 8 warps while the tile stays <= 3 columns wide
+    if (a.ncols <= 24) ct = (a.ncols + 7) / 8;
+    warps = (a.ncols + ct - 1) / ct;
+  } else {
+    pass1_shape(a.ncols, &ct, &warps);
+  }
+  if (warps > 16 || ct > 8) return cudaErrorInvalidValue;
+  if (pf && ct <= 3) {
+    switch (ct) {
+      case 1: return launch_fused_t<1, 2, true>(a, warps, num_sms, st, grid_mult);
+      case 2: return launch_fused_t<2, 2, true>(a, warps, num_sms, st, grid_mult);
+      default: return launch_fused_t<3, 2, true>(a, warps, num_sms, st, grid_mult);
+    }
+  }
   switch (ct) {
-    case 1: return launch_fused_t<1, 4>(a, warps, num_sms, st, grid_mult);
-    case 2: return launch_fused_t<2, 4>(a, warps, num_sms, st, grid_mult);
-    case 3: return launch_fused_t<3, 4>(a, warps, num_sms, st, grid_mult);
-    case 4: return launch_fused_t<4, 4>(a, warps, num_sms, st, grid_mult);
-    case 5: return launch_fused_t<5, 2>(a, warps, num_sms, st, grid_mult);
-    case 6: return launch_fused_t<6, 2>(a, warps, num_sms, st, grid_mult);
-    case 7: return launch_fused_t<7, 2>(a, warps, num_sms, st, grid_mult);
-    default: return launch_fused_t<8, 2>(a, warps, num_sms, st, grid_mult);
+    case 1: return launch_fused_t<1, 4, false>(a, warps, num_sms, st, grid_mult);
+    case 2: return launch_fused_t<2, 4, false>(a, warps, num_sms, st, grid_mult);
+    case 3: return launch_fused_t<3, 2, false>(a, warps, num_sms, st, grid_mult);
+    case 4: return launch_fused_t<4, 2, false>(a, warps, num_sms, st, grid_mult);
+    case 5: return launch_fused_t<5, 2, false>(a, warps, num_sms, st, grid_mult);
+    case 6: return launch_fused_t<6, 2, false>(a, warps, num_sms, st, grid_mult);
+    case 7: return launch_fused_t<7, 1, false>(a, warps, num_sms, st, grid_mult);
+    default: return launch_fused_t<8, 1, false>(a, warps, num_sms, st, grid_mult);
   }
 }
 

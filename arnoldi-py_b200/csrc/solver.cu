@@ -97,7 +97,8 @@ struct ab200_solver {
   PeerComm comm;
 
   // options
-  int opt_grid_mult = 0, opt_restart_variant = 0, opt_ortho_variant = 0, opt_spmv_tile = 0;
+  int opt_grid_mult = 0, opt_restart_variant = 0, opt_ortho_variant = 0, opt_spmv_tile = 0,
+      opt_fused_ct = 0;
 
   // stats
   bool timing = false;
@@ -238,7 +239,7 @@ static OrthoArgs make_ortho_args(ab200_solver* s, cplx* w, int ncols, int j, dou
 static int enqueue_ortho(ab200_solver* s, OrthoArgs a, int ortho_kind) {
   const double nb = 16.0 * (double)s->n;
   const int c = a.ncols;
-  if (ortho_kind == AB200_ORTHO_CGS2 && s->opt_ortho_variant == 0) {
+  if (ortho_kind == AB200_ORTHO_CGS2 && s->opt_ortho_variant != 1) {
     // default CGS2/DGKS schedule: 3 sweeps when the DGKS test fires, 2 when it does not
     a.round = 1;
     a.accumulate = 0;
@@ -248,7 +249,8 @@ static int enqueue_ortho(ab200_solver* s, OrthoArgs a, int ortho_kind) {
     }
     {
       LaunchScope ls(s, K_FUSED, a.j, 1, nb * (c + 2));
-      CU(launch_cgs_fused(a, s->num_sms, s->stream, s->opt_grid_mult));
+      CU(launch_cgs_fused(a, s->num_sms, s->stream, s->opt_grid_mult, s->opt_ortho_variant,
+                          s->opt_fused_ct));
     }
     a.round = 2;
     a.accumulate = 1;
@@ -707,6 +709,8 @@ int ab200_set_option(ab200_solver* s, const char* key, int64_t value) {
     s->opt_restart_variant = (int)value;
   else if (!strcmp(key, "ortho_variant"))
     s->opt_ortho_variant = (int)value;
+  else if (!strcmp(key, "fused_ct"))
+    s->opt_fused_ct = (int)value;
   else if (!strcmp(key, "spmv_tile"))
     s->opt_spmv_tile = (int)value;
   else
