@@ -353,8 +353,23 @@ __global__ void __launch_bounds__(256) cgs_pass2_kernel(OrthoArgs a) {
 // second round only needs its pass 2; if it does not, g' is simply dropped.  Same block
 // shape as pass 1: warp k owns columns [k*CT, k*CT+CT); the per-warp partial sums of
 // U coef meet in shared memory (double buffered: one __syncthreads per chunk).
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int sz = valid ? 16 : 0;  // src-size 0 => the 16 bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// PF = true: the block's NEXT chunk is staged into shared memory with cp.async (LDGSTS,
+// no registers held) while the current one is processed, so requests stay in flight across
+// the block barrier.  PF = false: plain register loads (more blocks per SM instead).
 template <int CT, int R, bool PF>
-__global__ void __launch_bounds__(CT < 8 && !(CT <= 3 && PF) ? 256 : 512) cgs_fused_kernel(OrthoArgs a) {
+__global__ void __launch_bounds__(CT < 8 ? 256 : 512) cgs_fused_kernel(OrthoArgs a) {
   StepCtl* ctl = a.ctl;
   if (ctl->stop) return;
 
@@ -366,6 +381,8 @@ __global__ void __launch_bounds__(CT < 8 && !(CT <= 3 && PF) ? 256 : 512) cgs_fu
   const int c = a.ncols;
   cplx* spart = reinterpret_cast<cplx*>(fused_smem);  // [2][nwarps][ROWS]
   cplx* scoef = spart + 2 * nwarps * ROWS;            // [nwarps * CT]
+  cplx* sw = scoef + nwarps * CT;                     // PF: [2][ROWS]           chunk of w
+  cplx* sv = sw + 2 * ROWS;                           // PF: [2][nwarps][CT][ROWS] chunk of U
   for (int i = threadIdx.x; i < nwarps * CT; i += blockDim.x)
     scoef[i] = i < c ? a.coef[i] : make_double2(0.0, 0.0);
   __syncthreads();
@@ -386,37 +403,75 @@ __global__ void __launch_bounds__(CT < 8 && !(CT <= 3 && PF) ? 256 : 512) cgs_fu
   double nacc = 0.0;
 
   const int64_t nchunks = (a.n + ROWS - 1) / ROWS;
-  // software pipeline: the loads of the block's next chunk are issued before the current
-  // chunk is processed, so every warp has requests in flight while it waits at the barrier
-  cplx wv[R], wn[R];
-  cplx v[CT][R], vn[CT][R];
-  auto load_chunk = [&](int64_t q, cplx(&ww)[R], cplx(&vv)[CT][R]) {
+  auto stage_v = [&](int64_t q, int b) {  // my columns of chunk q -> sv[b][warp]
     const int64_t base = q * ROWS + lane;
-    const bool full = q * ROWS + ROWS <= a.n;
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const bool ok = full || base + r * kWarp < a.n;
-      ww[r] = ok ? ld_coherent(w + base + r * kWarp) : make_double2(0.0, 0.0);
-    }
+    cplx* dst = sv + ((size_t)b * nwarps + warp) * CT * ROWS;
 #pragma unroll
     for (int k = 0; k < CT; ++k) {
       if (k < mycols) {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          const bool ok = full || base + r * kWarp < a.n;
-          vv[k][r] = ok ? ld_stream(U + (int64_t)k * ld + base + r * kWarp) : make_double2(0.0, 0.0);
+          const int64_t row = base + r * kWarp;
+          const bool ok = row < a.n;
+          cp_async16(dst + k * ROWS + r * kWarp + lane, U + (int64_t)k * ld + (ok ? row : 0), ok);
         }
       }
     }
   };
+  auto stage_w = [&](int64_t q, int b) {  // chunk q of w -> sw[b]   (warp 0 only)
+    const int64_t base = q * ROWS + lane;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int64_t row = base + r * kWarp;
+      const bool ok = row < a.n;
+      cp_async16(sw + (size_t)b * ROWS + r * kWarp + lane, w + (ok ? row : 0), ok);
+    }
+  };
+
   int buf = 0;
-  if (PF && (int64_t)blockIdx.x < nchunks) load_chunk(blockIdx.x, wv, v);
+  if (PF) {
+    if ((int64_t)blockIdx.x < nchunks) {
+      if (warp == 0) stage_w(blockIdx.x, 0);
+      stage_v(blockIdx.x, 0);
+    }
+    cp_async_commit();
+  }
   for (int64_t q = blockIdx.x; q < nchunks; q += gridDim.x, buf ^= 1) {
     const int64_t base = q * ROWS + lane;
     const bool full = q * ROWS + ROWS <= a.n;
     const int64_t qn = q + gridDim.x;
-    if (!PF) load_chunk(q, wv, v);
-    if (PF && qn < nchunks) load_chunk(qn, wn, vn);
+    cplx wv[R];
+    cplx v[CT][R];
+    if (PF) {
+      if (qn < nchunks) stage_v(qn, buf ^ 1);
+      cp_async_commit();
+      cp_async_wait<1>();  // everything but the group just committed has landed
+      __syncwarp();
+      const cplx* src = sv + ((size_t)buf * nwarps + warp) * CT * ROWS;
+#pragma unroll
+      for (int k = 0; k < CT; ++k)
+        if (k < mycols) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) v[k][r] = src[k * ROWS + r * kWarp + lane];
+        }
+    } else {
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const bool ok = full || base + r * kWarp < a.n;
+        wv[r] = ok ? ld_coherent(w + base + r * kWarp) : make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for (int k = 0; k < CT; ++k) {
+        if (k < mycols) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const bool ok = full || base + r * kWarp < a.n;
+            v[k][r] =
+                ok ? ld_stream(U + (int64_t)k * ld + base + r * kWarp) : make_double2(0.0, 0.0);
+          }
+        }
+      }
+    }
     // my columns' share of U coef for these rows
     cplx* mine = spart + ((size_t)buf * nwarps + warp) * ROWS;
 #pragma unroll
@@ -427,7 +482,14 @@ __global__ void __launch_bounds__(CT < 8 && !(CT <= 3 && PF) ? 256 : 512) cgs_fu
         if (k < mycols) cfma(t, v[k][r], cf[k]);
       mine[r * kWarp + lane] = t;
     }
-    __syncthreads();
+    __syncthreads();  // partial sums (and, PF, warp 0's chunk of w) visible to the block
+    if (PF) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) wv[r] = sw[(size_t)buf * ROWS + r * kWarp + lane];
+      // every warp is past its reads of sw[buf ^ 1] (previous chunk): refill it
+      if (warp == 0 && qn < nchunks) stage_w(qn, buf ^ 1);
+      cp_async_commit();
+    }
     // every warp rebuilds w' for the chunk (same order everywhere: bit-identical copies)
     const cplx* all = spart + (size_t)buf * nwarps * ROWS;
 #pragma unroll
@@ -455,15 +517,8 @@ __global__ void __launch_bounds__(CT < 8 && !(CT <= 3 && PF) ? 256 : 512) cgs_fu
         for (int r = 0; r < R; ++r) cfma_conj(acc[k], v[k][r], wv[r]);
       }
     }
-    if (PF && qn < nchunks) {
-#pragma unroll
-      for (int r = 0; r < R; ++r) wv[r] = wn[r];
-#pragma unroll
-      for (int k = 0; k < CT; ++k)
-#pragma unroll
-        for (int r = 0; r < R; ++r) v[k][r] = vn[k][r];
-    }
   }
+  if (PF) cp_async_wait<0>();
 
   const int gcap = a.grid_cap;
 #pragma unroll
@@ -680,11 +735,19 @@ static cudaError_t launch_fused_t(const OrthoArgs& a, int warps, int num_sms, cu
   OrthoArgs args = a;
   args.accumulate = 1;  // the dots it produces belong to round 2
   const int threads = warps * kWarp;
-  const int64_t nchunks = (a.n + kWarp * R - 1) / (kWarp * R);
-  size_t smem = sizeof(cplx) * ((size_t)2 * warps * kWarp * R + (size_t)warps * CT);
+  constexpr int ROWS = kWarp * R;
+  const int64_t nchunks = (a.n + ROWS - 1) / ROWS;
+  size_t smem = sizeof(cplx) * ((size_t)2 * warps * ROWS + (size_t)warps * CT);
+  if (PF) smem += sizeof(cplx) * ((size_t)2 * ROWS + (size_t)2 * warps * CT * ROWS);
   const size_t need = sizeof(double) * (2 * a.ncols + 2);
   if (smem < need) smem = need;
   static int occ[17] = {0};
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(cgs_fused_kernel<CT, R, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         200 * 1024);
+    attr_done = true;
+  }
   const int bps = grid_mult > 0 ? grid_mult
                                 : resident_blocks(cgs_fused_kernel<CT, R, PF>, threads, smem,
                                                   &occ[warps]);
@@ -693,30 +756,27 @@ static cudaError_t launch_fused_t(const OrthoArgs& a, int warps, int num_sms, cu
   return cudaGetLastError();
 }
 
-// variant: 0 = prefetching, narrow column tiles (<= 3 per warp, up to 16 warps);
-//          2 = no prefetch, pass-1 block shape;  fused_ct > 0 forces the tile width
+// variant 0: cp.async-staged (prefetching) kernel; variant 2: register loads only.
+// fused_ct > 0 forces the column-tile width (when the block shape allows it).
 cudaError_t launch_cgs_fused(const OrthoArgs& a, int num_sms, cudaStream_t st, int grid_mult,
                              int variant, int fused_ct) {
   int ct, warps;
-  const bool pf = (variant != 2);
-  if (fused_ct > 0) {
-    ct = fused_ct > 8 ? 8 : fused_ct;
-    warps = (a.ncols + ct - 1) / ct;
-  } else if (pf) {
-    ct = (a.ncols + 15) / 16;
-    if (ct < 1) ct = 1;
-    // prefer ~2 blocks of <= 8 warps while the tile stays <= 3 columns wide
-    if (a.ncols <= 24) ct = (a.ncols + 7) / 8;
-    warps = (a.ncols + ct - 1) / ct;
-  } else {
-    pass1_shape(a.ncols, &ct, &warps);
+  pass1_shape(a.ncols, &ct, &warps);
+  if (fused_ct > 0 && fused_ct <= 8) {
+    const int wf = (a.ncols + fused_ct - 1) / fused_ct;
+    if (wf <= (fused_ct < 8 ? 8 : 16)) ct = fused_ct, warps = wf;
   }
-  if (warps > 16 || ct > 8) return cudaErrorInvalidValue;
-  if (pf && ct <= 3) {
+  if (warps > 16) return cudaErrorInvalidValue;
+  if (variant != 2) {
     switch (ct) {
       case 1: return launch_fused_t<1, 2, true>(a, warps, num_sms, st, grid_mult);
       case 2: return launch_fused_t<2, 2, true>(a, warps, num_sms, st, grid_mult);
-      default: return launch_fused_t<3, 2, true>(a, warps, num_sms, st, grid_mult);
+      case 3: return launch_fused_t<3, 2, true>(a, warps, num_sms, st, grid_mult);
+      case 4: return launch_fused_t<4, 2, true>(a, warps, num_sms, st, grid_mult);
+      case 5: return launch_fused_t<5, 2, true>(a, warps, num_sms, st, grid_mult);
+      case 6: return launch_fused_t<6, 2, true>(a, warps, num_sms, st, grid_mult);
+      case 7: return launch_fused_t<7, 1, true>(a, warps, num_sms, st, grid_mult);
+      default: return launch_fused_t<8, 1, true>(a, warps, num_sms, st, grid_mult);
     }
   }
   switch (ct) {
