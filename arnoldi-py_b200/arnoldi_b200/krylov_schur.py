@@ -24,6 +24,12 @@ _ORTHO = {"cgs2": _lib.ORTHO_CGS2, "dgks_gs": _lib.ORTHO_CGS2, "mgs": _lib.ORTHO
           "dgks_mgs": _lib.ORTHO_MGS}
 
 
+def _as_scipy_csr(A):
+    import scipy.sparse as sp
+    indptr, indices, data, shape = as_csr(A)
+    return sp.csr_matrix((data, indices, indptr), shape=shape, copy=False)
+
+
 def _ortho_kind(ortho):
     if callable(ortho):
         ortho = getattr(ortho, "__name__", "")
@@ -36,7 +42,7 @@ def _ortho_kind(ortho):
 def partial_schur(
     A, nev, *, max_dim=None, stopping_criterion=None, max_restarts=100,
     sort_function=None, p=None,
-    ortho="cgs2", v0=None, device=0, stats=None, raise_on_no_convergence=True,
+    ortho="cgs2", v0=None, device=0, stats=None, raise_on_no_convergence=True, comm=None,
 ):
     """Partial Schur decomposition ``A Q = Q T`` of the ``nev`` wanted eigenvalues.
 
@@ -49,6 +55,10 @@ def partial_schur(
     stats : dict filled with true matvec count, DGKS rounds, per-kernel time/bytes
     raise_on_no_convergence : False returns the current (Q, T, history) instead of raising
         (used by the benchmark to time a bounded number of restart cycles)
+    comm  : a ``distributed.TorchComm`` (one process per GPU).  ``A`` is then either the whole
+        scipy CSR matrix (each rank slices its block of rows) or this rank's ``RowBlock``; every
+        rank must seed NumPy's global RNG identically (v0 is drawn globally and sliced); the
+        returned Q holds this rank's rows only, T and history are identical on all ranks.
 
     Returns ``(Q, T, history)``: Q (n, nev) complex128, T (nev, nev) complex128.
     """
@@ -69,18 +79,37 @@ def partial_schur(
     assert nev <= p < max_dim
     kind = _ortho_kind(ortho)
 
-    indptr, indices, data, _ = as_csr(A)
     H = np.zeros((max_dim + 1, max_dim), dtype=np.complex128)
     history = History.from_k(nev)
     converged = False
+    multi = comm is not None and comm.world > 1
+    if multi:
+        from .distributed import RowBlock, RowPartition, build_halo_plan, slice_rows
+        part = RowPartition(n, comm.world)
+        r0, r1 = part.rows(comm.rank)
+        block = A if isinstance(A, RowBlock) else slice_rows(_as_scipy_csr(A), r0, r1)
+        assert block.row0 == r0 and block.nrows == r1 - r0, "RowBlock does not match the partition"
+        plan = build_halo_plan(block)
+        solver_args = dict(device=device, row0=r0, nrows_local=r1 - r0)
+    else:
+        indptr, indices, data, _ = as_csr(A)
+        r0, r1 = 0, n
+        solver_args = dict(device=device)
 
-    with DeviceSolver(n, max_dim, device=device) as dev:
+    with DeviceSolver(n, max_dim, **solver_args) as dev:
         if stats is not None:
             dev.set_timing(True)
-        dev.set_csr(indptr, indices, data)
+        if multi:
+            dev.connect(comm, part)
+            dev.set_halo(plan.ghost_cols)
+            dev.set_csr(plan.indptr, plan.indices, plan.data)
+        else:
+            dev.set_csr(indptr, indices, data)
         if v0 is None:
             v0 = rand_normalized_vector(n, np.complex128)
-        dev.set_columns(0, v0)
+        dev.set_columns(0, v0[r0:r1])
+        if multi:
+            comm.barrier()   # every rank's column 0 is in place before any halo read
 
         def grow(start):
             cols, n_iter, _ = dev.expand(start, max_dim, tol, ortho=kind)
@@ -105,6 +134,8 @@ def partial_schur(
 
             # truncate
             dev.restart(Q, m, p)
+            if multi:
+                comm.barrier()   # peers read column p of this rank's block in the next SpMV
             H[:p, :p] = T2[:p, :p]
             H[p, :p] = spike
             H[p, p:] = 0
@@ -127,5 +158,7 @@ def partial_schur(
         if not converged and raise_on_no_convergence:
             raise ValueError("Has not converged !")
         Qout = dev.get_columns(0, nev)
+        if multi:
+            comm.barrier()   # nobody unmaps while a peer may still be in its last kernel
 
     return Qout, H[:nev, :nev].copy(), history

@@ -115,6 +115,22 @@ class DeviceSolver:
                                         float(eta), int(kind), C.byref(beta), C.byref(brk)))
         return beta.value, bool(brk.value)
 
+    # -- multi-GPU ---------------------------------------------------------------
+    def connect(self, comm, partition):
+        """Exchange CUDA-IPC handles with the other ranks (``comm`` = TorchComm-like) and map
+        their basis / reduction buffers.  Collective: every rank must call it."""
+        blob = C.create_string_buffer(256)
+        _lib.check(self.lib.ab200_comm_export(self._h, blob))
+        blobs = b"".join(comm.all_gather_bytes(blob.raw))
+        starts = np.ascontiguousarray(partition.starts, dtype=np.int64)
+        _lib.check(self.lib.ab200_comm_connect(self._h, int(comm.rank), int(comm.world), blobs,
+                                               _ptr(starts)))
+        comm.barrier()
+
+    def set_halo(self, ghost_cols):
+        g = np.ascontiguousarray(ghost_cols, dtype=np.int64)
+        _lib.check(self.lib.ab200_set_halo(self._h, _ptr(g), int(g.shape[0])))
+
     # -- measurement ------------------------------------------------------------
     def set_timing(self, on=True):
         _lib.check(self.lib.ab200_set_timing(self._h, int(bool(on))))

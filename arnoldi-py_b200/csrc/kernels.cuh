@@ -60,6 +60,20 @@ cudaError_t launch_spmv(const SpmvArgs& a, int indptr_bits, int value_kind, cuda
 cudaError_t launch_spmv_plan(const void* indptr, int indptr_bits, int64_t n, int64_t nnz, int tile,
                              int nblocks, int64_t* rowblk, cudaStream_t st);
 
+// ---------------------------------------------------------------- halo (multi-GPU)
+struct HaloArgs {
+  const cplx* peer_base[kMaxRanks];  // peer_base[q] = rank q's basis (IPC mapped; own pointer for q == rank)
+  int64_t peer_ld[kMaxRanks];        // leading dimension of rank q's basis
+  int64_t seg_start[kMaxRanks + 1];  // ghost entries [seg_start[q], seg_start[q+1]) are owned by rank q
+  const int64_t* src_off;            // [nghost] row offset inside the owner's block
+  cplx* ghost;                       // [nghost] destination
+  int64_t nghost;
+  int col;                           // basis column to fetch
+  int nranks;
+  const StepCtl* ctl;
+};
+cudaError_t launch_halo_gather(const HaloArgs& a, int num_sms, cudaStream_t st);
+
 // ---------------------------------------------------------------- restart + helpers
 struct RestartArgs {
   cplx* U;              // basis, updated in place

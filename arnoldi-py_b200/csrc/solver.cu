@@ -95,6 +95,19 @@ struct ab200_solver {
   int64_t n_local_cols = 0;
 
   PeerComm comm;
+  // multi-GPU state
+  int rank = 0, nranks = 1;
+  int64_t row_starts[kMaxRanks + 1] = {0};
+  double* slots = nullptr;                 // my receive area: [2][kMaxRanks][slot_doubles]
+  unsigned long long* flags = nullptr;     // my flags: [2][kMaxRanks]
+  unsigned long long* seq = nullptr;       // exchange counter
+  void* peer_V[kMaxRanks] = {nullptr};     // IPC mappings (nullptr for self / unused)
+  void* peer_slots[kMaxRanks] = {nullptr};
+  void* peer_flags[kMaxRanks] = {nullptr};
+  int64_t peer_ld[kMaxRanks] = {0};
+  int64_t* ghost_off = nullptr;            // [nghost] offsets inside the owner's block
+  int64_t nghost = 0;
+  int64_t seg_start[kMaxRanks + 1] = {0};
 
   // options
   int opt_grid_mult = 0, opt_restart_variant = 0, opt_ortho_variant = 0, opt_spmv_tile = 0,
@@ -308,7 +321,13 @@ int ab200_destroy(ab200_solver* s) {
   cudaFree(s->hscratch), cudaFree(s->coef), cudaFree(s->part), cudaFree(s->npart);
   cudaFree(s->ticket), cudaFree(s->ctl), cudaFree(s->step_round2), cudaFree(s->qdev);
   cudaFree(s->indptr), cudaFree(s->indices), cudaFree(s->values), cudaFree(s->rowblk);
-  cudaFree(s->ghost);
+  cudaFree(s->ghost), cudaFree(s->ghost_off);
+  for (int r = 0; r < kMaxRanks; ++r) {
+    if (s->peer_V[r]) cudaIpcCloseMemHandle(s->peer_V[r]);
+    if (s->peer_slots[r]) cudaIpcCloseMemHandle(s->peer_slots[r]);
+    if (s->peer_flags[r]) cudaIpcCloseMemHandle(s->peer_flags[r]);
+  }
+  cudaFree(s->slots), cudaFree(s->flags), cudaFree(s->seq);
   cudaFreeHost(s->h_H), cudaFreeHost(s->h_scale), cudaFreeHost(s->h_ctl);
   cudaFreeHost(s->h_step_round2), cudaFreeHost(s->h_q);
   if (s->stream) cudaStreamDestroy(s->stream);
@@ -495,8 +514,26 @@ static int enqueue_spmv(ab200_solver* s, const cplx* x, cplx* y, const double* x
   a.tile = s->tile;
   a.ctl = in_expand ? s->ctl : nullptr;
   const double sv = s->value_kind == AB200_F64 ? 8.0 : 16.0;
-  const double bytes = (double)s->nnz * (sv + 4.0) + (double)s->n * (s->indptr_bits / 8 + 32.0);
+  const double bytes = (double)s->nnz * (sv + 4.0) + (double)s->n * (s->indptr_bits / 8 + 32.0) +
+                       32.0 * (double)s->nghost;
   LaunchScope ls(s, K_SPMV, step, 0, bytes);
+  if (s->nghost > 0) {
+    if (!in_expand) return set_err(AB200_ESTATE, "halo SpMV is only available inside ab200_expand");
+    HaloArgs h;
+    for (int r = 0; r < kMaxRanks; ++r) {
+      h.peer_base[r] = r == s->rank ? s->V : static_cast<const cplx*>(s->peer_V[r]);
+      h.peer_ld[r] = s->peer_ld[r];
+    }
+    for (int r = 0; r <= kMaxRanks; ++r) h.seg_start[r] = s->seg_start[r];
+    h.src_off = s->ghost_off;
+    h.ghost = s->ghost;
+    h.nghost = s->nghost;
+    h.col = step;
+    h.nranks = s->nranks;
+    h.ctl = s->ctl;
+    CU(launch_halo_gather(h, s->num_sms, s->stream));
+    s->st.kernel_launches += 1;
+  }
   CU(launch_spmv(a, s->indptr_bits, s->value_kind, s->stream));
   return AB200_OK;
 }
@@ -645,6 +682,115 @@ int ab200_ortho(ab200_solver* s, int ncols, double* w_host, double* h_host, doub
   *breakdown = (*beta < tol) ? 1 : 0;
   s->st.ortho_rounds = s->h_ctl->rounds_total;
   s->st.second_rounds = s->h_ctl->second_total;
+  return AB200_OK;
+}
+
+struct CommBlob {
+  cudaIpcMemHandle_t v, slots, flags;
+  int64_t ld;
+  int64_t n;
+  int max_dim;
+  int magic;
+};
+static_assert(sizeof(CommBlob) <= AB200_COMM_BLOB_BYTES, "blob too large");
+static const int kSlotDoubles = 2 * 129 + 8;
+
+int ab200_comm_export(ab200_solver* s, void* blob) {
+  REQUIRE(s != nullptr && blob != nullptr, "null argument");
+  CU(cudaSetDevice(s->device));
+  if (!s->slots) {
+    CU(cudaMalloc(&s->slots, sizeof(double) * 2 * kMaxRanks * kSlotDoubles));
+    CU(cudaMalloc(&s->flags, sizeof(unsigned long long) * 2 * kMaxRanks));
+    CU(cudaMalloc(&s->seq, sizeof(unsigned long long)));
+    CU(cudaMemset(s->slots, 0, sizeof(double) * 2 * kMaxRanks * kSlotDoubles));
+    CU(cudaMemset(s->flags, 0, sizeof(unsigned long long) * 2 * kMaxRanks));
+    CU(cudaMemset(s->seq, 0, sizeof(unsigned long long)));
+    CU(cudaDeviceSynchronize());
+  }
+  CommBlob b;
+  memset(&b, 0, sizeof(b));
+  CU(cudaIpcGetMemHandle(&b.v, s->V));
+  CU(cudaIpcGetMemHandle(&b.slots, s->slots));
+  CU(cudaIpcGetMemHandle(&b.flags, s->flags));
+  b.ld = s->ld;
+  b.n = s->n;
+  b.max_dim = s->max_dim;
+  b.magic = 0xab200;
+  memset(blob, 0, AB200_COMM_BLOB_BYTES);
+  memcpy(blob, &b, sizeof(b));
+  return AB200_OK;
+}
+
+int ab200_comm_connect(ab200_solver* s, int rank, int nranks, const void* blobs,
+                       const int64_t* row_starts) {
+  REQUIRE(s != nullptr && blobs != nullptr && row_starts != nullptr, "null argument");
+  REQUIRE(nranks >= 1 && nranks <= kMaxRanks && rank >= 0 && rank < nranks,
+          "need 0 <= rank (%d) < nranks (%d) <= %d", rank, nranks, kMaxRanks);
+  if (!s->slots) return set_err(AB200_ESTATE, "ab200_comm_connect before ab200_comm_export");
+  REQUIRE(row_starts[0] == 0 && row_starts[nranks] == s->n_global, "row_starts must span [0, n_global]");
+  REQUIRE(row_starts[rank] == s->row0 && row_starts[rank + 1] == s->row0 + s->n,
+          "row_starts[rank] does not match this solver's row block");
+  CU(cudaSetDevice(s->device));
+  const unsigned char* bl = static_cast<const unsigned char*>(blobs);
+  for (int r = 0; r < nranks; ++r) {
+    CommBlob b;
+    memcpy(&b, bl + (size_t)r * AB200_COMM_BLOB_BYTES, sizeof(b));
+    REQUIRE(b.magic == 0xab200 && b.max_dim == s->max_dim, "blob of rank %d is not from a matching solver", r);
+    REQUIRE(b.n == row_starts[r + 1] - row_starts[r], "blob of rank %d has %lld rows, partition says %lld", r,
+            (long long)b.n, (long long)(row_starts[r + 1] - row_starts[r]));
+    s->peer_ld[r] = b.ld;
+    s->row_starts[r] = row_starts[r];
+    if (r == rank) {
+      s->comm.slots[r] = s->slots;
+      s->comm.flags[r] = s->flags;
+      continue;
+    }
+    CU(cudaIpcOpenMemHandle(&s->peer_V[r], b.v, cudaIpcMemLazyEnablePeerAccess));
+    CU(cudaIpcOpenMemHandle(&s->peer_slots[r], b.slots, cudaIpcMemLazyEnablePeerAccess));
+    CU(cudaIpcOpenMemHandle(&s->peer_flags[r], b.flags, cudaIpcMemLazyEnablePeerAccess));
+    s->comm.slots[r] = static_cast<double*>(s->peer_slots[r]);
+    s->comm.flags[r] = static_cast<unsigned long long*>(s->peer_flags[r]);
+  }
+  s->row_starts[nranks] = row_starts[nranks];
+  s->rank = rank;
+  s->nranks = nranks;
+  s->comm.nranks = nranks;
+  s->comm.rank = rank;
+  s->comm.slot_doubles = kSlotDoubles;
+  s->comm.seq = s->seq;
+  return AB200_OK;
+}
+
+int ab200_set_halo(ab200_solver* s, const int64_t* ghost_cols, int64_t nghost) {
+  REQUIRE(s != nullptr && nghost >= 0 && (nghost == 0 || ghost_cols != nullptr), "bad argument");
+  if (nghost > 0 && s->nranks <= 1)
+    return set_err(AB200_ESTATE, "ab200_set_halo with ghost columns needs ab200_comm_connect first");
+  CU(cudaSetDevice(s->device));
+  CU(cudaStreamSynchronize(s->stream));
+  cudaFree(s->ghost), cudaFree(s->ghost_off);
+  s->ghost = nullptr, s->ghost_off = nullptr, s->nghost = 0;
+  if (nghost == 0) return AB200_OK;
+  std::vector<int64_t> off((size_t)nghost);
+  int q = 0;
+  for (int r = 0; r <= kMaxRanks; ++r) s->seg_start[r] = nghost;
+  s->seg_start[0] = 0;
+  int64_t prev = -1;
+  for (int64_t k = 0; k < nghost; ++k) {
+    const int64_t g = ghost_cols[k];
+    REQUIRE(g > prev && g >= 0 && g < s->n_global, "ghost_cols must be strictly increasing in [0, n)");
+    REQUIRE(g < s->row0 || g >= s->row0 + s->n, "ghost column %lld is inside the local block", (long long)g);
+    prev = g;
+    while (g >= s->row_starts[q + 1]) {
+      ++q;
+      s->seg_start[q] = k;
+    }
+    off[(size_t)k] = g - s->row_starts[q];
+  }
+  for (int r = q + 1; r <= kMaxRanks; ++r) s->seg_start[r] = nghost;
+  CU(cudaMalloc(&s->ghost, sizeof(cplx) * (size_t)nghost));
+  CU(cudaMalloc(&s->ghost_off, sizeof(int64_t) * (size_t)nghost));
+  CU(cudaMemcpy(s->ghost_off, off.data(), sizeof(int64_t) * (size_t)nghost, cudaMemcpyHostToDevice));
+  s->nghost = nghost;
   return AB200_OK;
 }
 

@@ -373,7 +373,140 @@ def traffic_from_profile(kernel, grid):
 
 
 def run_b200_multi(args, rank, world, local):
-    raise SystemExit("multi-GPU bench not wired yet")
+    """Strong scaling on one box: the SAME config-2 solve, rows of A and V block-row
+    sharded over `world` GPUs (one process each); halo of v pulled from peer HBM over
+    NVLink inside the SpMV's gather kernel, inner products combined inside the reducing
+    kernels over peer memory.  torch.distributed (NCCL) only bootstraps and takes the max
+    of the per-rank timings."""
+    import torch
+    import torch.distributed as dist
+    from scipy.linalg import schur
+
+    from arnoldi_b200 import _lib, partial_schur
+    from arnoldi_b200.distributed import RowPartition, TorchComm, build_halo_plan, slice_rows
+    from arnoldi_b200.matrices import lap2d
+    from arnoldi_b200.solver import DeviceSolver
+    from arnoldi_b200.utils import arg_largest_real, ordered_schur, rand_normalized_vector
+
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl")
+    comm = TorchComm()
+    grid = args.grid
+    A = lap2d(grid)
+    n = A.shape[0]
+    part = RowPartition(n, world)
+    r0, r1 = part.rows(rank)
+    plan = build_halo_plan(slice_rows(A, r0, r1))
+    np.random.seed(0)
+    v0 = rand_normalized_vector(n, np.complex128)
+    H = np.zeros((MAX_DIM + 1, MAX_DIM), np.complex128)
+
+    dev = DeviceSolver(n, MAX_DIM, device=local, row0=r0, nrows_local=r1 - r0)
+    dev.set_timing(True)
+    dev.connect(comm, part)
+    dev.set_halo(plan.ghost_cols)
+    dev.set_csr(plan.indptr, plan.indices, plan.data)
+    dev.set_columns(0, v0[r0:r1])
+    comm.barrier()
+
+    def grow(start):
+        cols, n_iter, brk = dev.expand(start, MAX_DIM, TOL)
+        assert n_iter == MAX_DIM and not brk
+        for j in range(start, n_iter):
+            H[: j + 2, j] = cols[: j + 2, j]
+
+    def cycle():
+        m = MAX_DIM
+        T1, Q1 = schur(H[:m, :m], output="complex")
+        T2, Q2 = ordered_schur(T1, output="complex", sort_function=arg_largest_real)
+        Q = Q1 @ Q2
+        spike = H[m, :m] @ Q[:, :P]
+        dev.restart(Q, m, P)
+        comm.barrier()
+        H[:P, :P] = T2[:P, :P]
+        H[P, :P] = spike
+        H[P, P:] = 0
+        grow(P)
+
+    grow(0)
+    for _ in range(max(3, args.warmup)):
+        cycle()
+    dev.synchronize()
+    dev.reset_stats()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    comm.barrier()
+    dev.timer_start()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cycle()
+    ms = dev.timer_stop()
+    wall = time.perf_counter() - t0
+    comm.barrier()
+    clk = clocks.stop() if rank == 0 else None
+    ms_max = comm.max_float(ms)
+    wall_max = comm.max_float(wall)
+    st = dev.stats()
+    matvecs = args.steps * (MAX_DIM - P)
+    value = matvecs / (ms_max * 1e-3)
+    peak, peak_src = measured_peak()
+    classes = {}
+    for key in ("spmv", "ortho_pass1", "ortho_fused", "ortho_pass2", "restart"):
+        if st[key + "_launches"]:
+            classes[key] = dict(ms=st[key + "_ms"], bytes=st[key + "_bytes"],
+                                launches=st[key + "_launches"],
+                                gbs=st[key + "_bytes"] / st[key + "_ms"] / 1e6)
+    top = max(classes, key=lambda k: classes[k]["ms"])
+    kernels = {k: {"launches": v["launches"], "avg_ms": v["ms"] / v["launches"],
+                   "achieved_gbs": v["gbs"], "frac_of_measured": v["gbs"] / peak,
+                   "share_of_step": v["ms"] / ms} for k, v in classes.items()}
+    roofline = {"bound": "hbm", "kernel": top, "achieved": classes[top]["gbs"], "peak": peak,
+                "unit": "GB/s", "frac": classes[top]["gbs"] / peak, "peak_source": peak_src,
+                "traffic": None, "kernels": kernels, "note": "rank 0, per-GPU bytes / per-GPU time",
+                "halo_entries_rank0": int(len(plan.ghost_cols))}
+    launches = int(st["kernel_launches"])
+    dev.close()
+
+    e2e = None
+    if not args.no_e2e:
+        restarts = args.e2e_restarts
+        h2d = plan.data.nbytes + plan.indices.nbytes + plan.indptr.nbytes + 16 * (r1 - r0)
+        d2h = 16 * (r1 - r0) * NEV + 16 * (MAX_DIM + 1) * MAX_DIM
+        times = []
+        mv = 0
+        for rep in range(args.e2e_reps + 1):
+            np.random.seed(0)
+            stats = {}
+            comm.barrier()
+            t0 = time.perf_counter()
+            partial_schur(A, NEV, max_dim=MAX_DIM, stopping_criterion=TOL,
+                          sort_function=arg_largest_real, max_restarts=restarts,
+                          raise_on_no_convergence=False, stats=stats, device=local, comm=comm)
+            dt = comm.max_float(time.perf_counter() - t0)
+            if rep > 0:
+                times.append(dt)
+            mv = stats["true_matvecs"]
+        e2e = {"value": mv / float(np.mean(times)), "unit": UNIT,
+               "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
+               "call": f"partial_schur(A_host, {NEV}, max_dim={MAX_DIM}, max_restarts={restarts}, "
+                       f"comm=...) = {mv} matvecs per call, {float(np.mean(times)):.3f} s per call "
+                       "(max over ranks) incl. row slicing + halo plan on the host, uploads, "
+                       "local Q download", "reps": len(times)}
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_max / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "c128",
+            "data": "synthetic", "config": dict(workload_config(), parallelism=f"block-row x{world}")
+            if grid == GRID_FULL else {"workload": f"lap2d({grid}) REDUCED (not config 2)"},
+            "wall_ms_per_step": 1e3 * wall_max / args.steps,
+            "roofline": roofline, "cpu_baseline": None, "e2e": e2e,
+            "gpu_launches": launches, "clocks": clk,
+        }
+        print(json.dumps(line))
+    comm.barrier()
+    dist.destroy_process_group()
 
 
 def main():

@@ -129,6 +129,31 @@ int ab200_spmv(ab200_solver *s, const double *x_host, double *y_host);
 int ab200_ortho(ab200_solver *s, int ncols, double *w_host, double *h_host, double tol,
                 double eta, int ortho_kind, double *beta, int *breakdown);
 
+/* ---- one box, several GPUs: block-row shards, one process per GPU ----
+ * The reference has no distributed path; these calls carry the
+ * north star's sharding.  Bootstrap (exchanging the opaque blobs below between the
+ * processes) is the caller's job -- the Python driver uses torch.distributed.
+ *
+ * ab200_comm_export  writes this rank's AB200_COMM_BLOB_BYTES-byte blob (CUDA IPC handles of
+ *                    its basis, reduction slots and flags, plus its leading dimension).
+ * ab200_comm_connect takes every rank's blob (rank-major) and the row partition
+ *                    row_starts[0..nranks]; maps the peers' memory.  After it, every
+ *                    reduction inside ab200_expand / ab200_ortho is a global one (partials
+ *                    pushed to all peers over NVLink inside the reducing kernel, summed in rank
+ *                    order: identical bits on every rank) and all ranks must make the same
+ *                    sequence of calls.
+ * ab200_set_halo     declares which remote entries of v the local CSR block reads: ghost_cols
+ *                    are GLOBAL column ids, strictly increasing, none inside the local block.
+ *                    The CSR passed to ab200_set_csr must then use LOCAL column numbering:
+ *                    id < nrows_local = local row id, id >= nrows_local = nrows_local + index
+ *                    into ghost_cols.  */
+#define AB200_COMM_BLOB_BYTES 256
+#define AB200_MAX_RANKS 8
+int ab200_comm_export(ab200_solver *s, void *blob);
+int ab200_comm_connect(ab200_solver *s, int rank, int nranks, const void *blobs,
+                       const int64_t *row_starts);
+int ab200_set_halo(ab200_solver *s, const int64_t *ghost_cols, int64_t nghost);
+
 /* ---- measurement ---- */
 int ab200_set_timing(ab200_solver *s, int enabled); /* CUDA-event timing per kernel class */
 int ab200_reset_stats(ab200_solver *s);

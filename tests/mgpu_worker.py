@@ -1,0 +1,69 @@
+"""Multi-GPU parity worker: run under torchrun, one rank per GPU.
+
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/mgpu_worker.py
+
+Every rank solves the same seeded problems as tests/golden/solves.npz through the sharded
+path and rank 0 checks the gathered result against the reference's record."""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+for p in (ROOT, os.path.join(ROOT, "arnoldi-py_b200"), HERE):
+    sys.path.insert(0, p)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ["RANK"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl")
+    from arnoldi_b200 import partial_schur
+    from arnoldi_b200.distributed import RowPartition, TorchComm
+    from arnoldi_b200.matrices import lap2d, mark
+    from arnoldi_b200.utils import arg_largest_real
+    comm = TorchComm()
+    g = np.load(os.path.join(HERE, "golden", "solves.npz"))
+    cases = [("mark50_s0", mark(50), dict(nev=5, max_dim=20), "cgs2"),
+             ("mark100_s0", mark(100), dict(nev=20, max_dim=60), "cgs2"),
+             ("mark50_mgs_s0", mark(50), dict(nev=5, max_dim=20), "mgs")]
+    from conftest import lap2d as lap2d_kron
+    cases.append(("lap2d64_s0", lap2d_kron(64), dict(nev=10, max_dim=40), "cgs2"))
+    for tag, A, kw, ortho in cases:
+        n = A.shape[0]
+        np.random.seed(0)
+        stats = {}
+        Q, T, hist = partial_schur(A, kw["nev"], max_dim=kw["max_dim"], stopping_criterion=1e-8,
+                                   max_restarts=1000, sort_function=arg_largest_real,
+                                   ortho=ortho, device=local, comm=comm, stats=stats)
+        part = RowPartition(n, comm.world)
+        r0, r1 = part.rows(rank)
+        assert Q.shape == (r1 - r0, kw["nev"])
+        pieces = comm.all_gather_bytes(np.ascontiguousarray(Q).tobytes())
+        Ts = comm.all_gather_bytes(T.tobytes())
+        assert all(t == Ts[0] for t in Ts), "T differs between ranks"      # identical bits
+        if rank == 0:
+            Qf = np.concatenate([np.frombuffer(b, np.complex128).reshape(-1, kw["nev"])
+                                 for b in pieces])
+            lam, ref = np.diag(T), g[f"{tag}_diagT"]
+            rel = np.abs(lam - ref) / np.abs(ref)
+            res = np.linalg.norm(A @ Qf - Qf @ T, axis=0)
+            R, Rref = int(hist.restarts[0]), int(g[f"{tag}_hist_restarts"][0])
+            assert abs(R - Rref) <= 2, (tag, R, Rref)
+            assert np.sum(rel > 1e-10) <= max(1, len(lam) // 10) and rel.max() < 1e-8, (tag, rel)
+            assert res.max() < 1e-7, (tag, res)
+            assert np.abs(Qf.conj().T @ Qf - np.eye(kw["nev"])).max() < 1e-12
+            print(f"[mgpu] {tag}: world={comm.world} R={R} (ref {Rref}) max rel {rel.max():.2e} "
+                  f"res {res.max():.2e} second_rounds={stats['second_rounds']}", flush=True)
+    comm.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("[mgpu] OK", flush=True)
+
+
+if __name__ == "__main__":
+    main()
