@@ -58,7 +58,7 @@ __device__ void peer_allreduce(const PeerComm& pc, double* red, int count, StepC
     volatile unsigned long long* f = pc.flags[pc.rank] + (size_t)par * kMaxRanks + tid;
     long long spins = 0;
     while (*f < seq) {
-      if (++spins > (1ll << 31)) {
+      if (++spins > (1ll << 26)) {  // ~tens of seconds: a peer died or diverged
         ctl->comm_error = 1;
         break;
       }
