@@ -85,13 +85,15 @@ class HaloPlan:
 
 def build_halo_plan(block: RowBlock) -> HaloPlan:
     r0, nloc = block.row0, block.nrows
-    idx = np.asarray(block.indices, dtype=np.int64)
+    idx = np.asarray(block.indices)
     local = (idx >= r0) & (idx < r0 + nloc)
-    ghost = np.unique(idx[~local])
+    outside = idx[~local].astype(np.int64)          # usually a tiny fraction of the entries
+    ghost = np.unique(outside)
     assert nloc + ghost.shape[0] < 2**31, "local + ghost columns exceed int32"
-    renum = np.where(local, idx - r0, nloc + np.searchsorted(ghost, idx)).astype(np.int32)
-    return HaloPlan(np.asarray(block.indptr), renum, np.asarray(block.data), ghost.astype(np.int64),
-                    r0, nloc)
+    renum = (idx - r0).astype(np.int32)              # wraps for outside entries: overwritten next
+    if outside.shape[0]:
+        renum[~local] = (nloc + np.searchsorted(ghost, outside)).astype(np.int32)
+    return HaloPlan(np.asarray(block.indptr), renum, np.asarray(block.data), ghost, r0, nloc)
 
 
 class TorchComm:

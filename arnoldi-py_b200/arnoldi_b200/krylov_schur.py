@@ -79,6 +79,17 @@ def partial_schur(
     assert nev <= p < max_dim
     kind = _ortho_kind(ortho)
 
+    import time
+    clock = time.perf_counter
+    phases = {}
+    t_mark = clock()
+
+    def lap(name):
+        nonlocal t_mark
+        now = clock()
+        phases[name] = phases.get(name, 0.0) + (now - t_mark)
+        t_mark = now
+
     H = np.zeros((max_dim + 1, max_dim), dtype=np.complex128)
     history = History.from_k(nev)
     converged = False
@@ -96,7 +107,9 @@ def partial_schur(
         r0, r1 = 0, n
         solver_args = dict(device=device)
 
+    lap("host_prepare")
     with DeviceSolver(n, max_dim, **solver_args) as dev:
+        lap("device_alloc")
         if stats is not None:
             dev.set_timing(True)
         if multi:
@@ -105,8 +118,10 @@ def partial_schur(
             dev.set_csr(plan.indptr, plan.indices, plan.data)
         else:
             dev.set_csr(indptr, indices, data)
+        lap("upload_csr")
         if v0 is None:
             v0 = rand_normalized_vector(n, np.complex128)
+        lap("host_v0")
         dev.set_columns(0, v0[r0:r1])
         if multi:
             comm.barrier()   # every rank's column 0 is in place before any halo read
@@ -117,7 +132,9 @@ def partial_schur(
                 H[: j + 2, j] = cols[: j + 2, j]
             return n_iter
 
+        lap("upload_v0")
         m = grow(0)
+        lap("expand")
         for restart in range(max_restarts):
             if m != max_dim:
                 raise ValueError("Happy breakdown not supported yet")
@@ -132,10 +149,12 @@ def partial_schur(
             spike = H[m, :m] @ Qp
             last_beta = H[m, m - 1]
 
+            lap("host_schur")
             # truncate
             dev.restart(Q, m, p)
             if multi:
                 comm.barrier()   # peers read column p of this rank's block in the next SpMV
+            lap("restart")
             H[:p, :p] = T2[:p, :p]
             H[p, :p] = spike
             H[p, p:] = 0
@@ -149,6 +168,7 @@ def partial_schur(
                 converged = True
                 break
             m = grow(p)
+            lap("expand")
 
         if stats is not None:
             stats.update(dev.stats())
@@ -157,8 +177,13 @@ def partial_schur(
             stats["converged"] = converged
         if not converged and raise_on_no_convergence:
             raise ValueError("Has not converged !")
+        lap("host_schur")
         Qout = dev.get_columns(0, nev)
+        lap("download_q")
         if multi:
             comm.barrier()   # nobody unmaps while a peer may still be in its last kernel
+    lap("device_free")
+    if stats is not None:
+        stats["host_phases_s"] = phases
 
     return Qout, H[:nev, :nev].copy(), history

@@ -341,7 +341,8 @@ def run_b200(args):
                "call": f"partial_schur(A_host, {NEV}, max_dim={MAX_DIM}, max_restarts={restarts}) "
                        f"= {mv} matvecs per call, {float(np.mean(times)):.3f} s per call incl. "
                        "v0 = randn(n) on the host, CSR upload from pinned memory, Q/T download",
-               "reps": len(times)}
+               "reps": len(times),
+               "host_phases_s": {k: round(v, 4) for k, v in out.get("host_phases_s", {}).items()}}
         for ptr in keep:
             lib.ab200_host_free(ptr)
 
@@ -487,12 +488,14 @@ def run_b200_multi(args, rank, world, local):
             if rep > 0:
                 times.append(dt)
             mv = stats["true_matvecs"]
+            phases = stats.get("host_phases_s", {})
         e2e = {"value": mv / float(np.mean(times)), "unit": UNIT,
                "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
                "call": f"partial_schur(A_host, {NEV}, max_dim={MAX_DIM}, max_restarts={restarts}, "
                        f"comm=...) = {mv} matvecs per call, {float(np.mean(times)):.3f} s per call "
                        "(max over ranks) incl. row slicing + halo plan on the host, uploads, "
-                       "local Q download", "reps": len(times)}
+                       "local Q download", "reps": len(times),
+               "host_phases_s_rank0": {k: round(v, 4) for k, v in phases.items()}}
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
