@@ -14,12 +14,14 @@ from . import _lib
 from .solver import DeviceSolver
 
 
-def _run(kind, w, V, h, tol, eta, device):
+def _run(kind, w, V, h, tol, eta, device, options=None):
     n, c = V.shape
     assert w.shape == (n,) and h.shape[0] >= c
     wbuf = np.ascontiguousarray(w, dtype=np.complex128)
     hbuf = np.zeros(c, np.complex128)
     with DeviceSolver(n, max(c, 1), device=device) as dev:
+        for key, value in (options or {}).items():
+            dev.set_option(key, value)
         dev.set_columns(0, V)
         beta, broke = dev.ortho(c, wbuf, hbuf, tol, eta, kind)
     w[:] = wbuf
@@ -27,9 +29,9 @@ def _run(kind, w, V, h, tol, eta, device):
     return beta, broke
 
 
-def dgks_gs(w, V, h, tol=1e-8, eta=np.sqrt(0.5), *, device=0):
+def dgks_gs(w, V, h, tol=1e-8, eta=np.sqrt(0.5), *, device=0, options=None):
     """Classical Gram-Schmidt, repeated once when the DGKS test fires (ortho.py:56-107)."""
-    return _run(_lib.ORTHO_CGS2, w, V, h, tol, eta, device)
+    return _run(_lib.ORTHO_CGS2, w, V, h, tol, eta, device, options)
 
 
 def dgks_mgs(w, V, h, tol=1e-8, eta=np.sqrt(0.5), *, device=0):

@@ -119,6 +119,9 @@ struct ab200_solver {
   std::vector<cudaEvent_t> pool;
   ab200_stats st;
   cudaEvent_t t0 = nullptr, t1 = nullptr;
+  // DGKS history: did the second round run on most steps of the last expansion?  Decides
+  // between the 3-sweep schedule (pass 1, fused, pass 2) and the 2(+2)-sweep one.
+  bool dgks_hot = false;
 };
 
 static cudaEvent_t get_event(ab200_solver* s) {
@@ -252,7 +255,8 @@ static OrthoArgs make_ortho_args(ab200_solver* s, cplx* w, int ncols, int j, dou
 static int enqueue_ortho(ab200_solver* s, OrthoArgs a, int ortho_kind) {
   const double nb = 16.0 * (double)s->n;
   const int c = a.ncols;
-  if (ortho_kind == AB200_ORTHO_CGS2 && s->opt_ortho_variant != 1) {
+  const bool fuse = s->opt_ortho_variant == 0 ? s->dgks_hot : s->opt_ortho_variant != 1;
+  if (ortho_kind == AB200_ORTHO_CGS2 && fuse) {
     // default CGS2/DGKS schedule: 3 sweeps when the DGKS test fires, 2 when it does not
     a.round = 1;
     a.accumulate = 0;
@@ -591,6 +595,11 @@ int ab200_expand(ab200_solver* s, int start_dim, int end_dim, double tol, double
   s->st.arnoldi_steps = s->h_ctl->steps_total;
   s->st.ortho_rounds = s->h_ctl->rounds_total;
   s->st.second_rounds = s->h_ctl->second_total;
+  if (done > start_dim) {
+    int fired = 0;
+    for (int j = start_dim; j < done; ++j) fired += s->h_step_round2[j] ? 1 : 0;
+    s->dgks_hot = 2 * fired > (done - start_dim);
+  }
   return AB200_OK;
 }
 

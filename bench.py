@@ -519,8 +519,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--grid", type=int, default=GRID_FULL, help="lap2d grid side (4096 = config 2)")
-    ap.add_argument("--e2e-restarts", type=int, default=8)
-    ap.add_argument("--e2e-reps", type=int, default=2)
+    ap.add_argument("--e2e-restarts", type=int, default=24)
+    ap.add_argument("--e2e-reps", type=int, default=1)
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -163,8 +163,14 @@ int ab200_synchronize(ab200_solver *s);
  * the elapsed milliseconds of everything enqueued in between (after it has finished). */
 int ab200_timer_start(ab200_solver *s);
 int ab200_timer_stop(ab200_solver *s, double *elapsed_ms);
-/* Select kernel variants (for A/B measurements): key is one of "spmv_lanes",
- * "ortho_variant", "restart_variant", "grid_mult", "spmv_tile"; value 0 = automatic. */
+/* Select kernel variants (for A/B measurements); value 0 = automatic.
+ *   "ortho_variant"   CGS2 schedule: 0 = adaptive (fused sweep while the DGKS test fires on
+ *                     most steps, two-sweep rounds otherwise), 1 = always two-sweep rounds,
+ *                     2 = always fused (register loads), 3 = always fused (cp.async staging)
+ *   "fused_ct"        column-tile width of the fused sweep (1..8)
+ *   "restart_variant" outputs per warp of the restart kernel (4, 8, 16)
+ *   "grid_mult"       resident blocks per SM for the orthogonalisation kernels
+ *   "spmv_tile"       non-zeros staged per SpMV block (takes effect at the next ab200_set_csr) */
 int ab200_set_option(ab200_solver *s, const char *key, int64_t value);
 
 /* Pinned host memory for callers that want asynchronous, full-speed uploads. */
