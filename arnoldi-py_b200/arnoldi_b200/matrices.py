@@ -72,3 +72,90 @@ def lap2d(N):
     cols = np.stack([idx - N, idx - 1, idx, idx + 1, idx + N], axis=1).astype(it)[keep]
     vals = np.broadcast_to(np.array([-1.0, -1.0, 4.0, -1.0, -1.0]), (n, 5))[keep]
     return sp.csr_matrix((vals, cols, indptr.astype(it)), shape=(n, n))
+
+
+# ----------------------------------------------------------------------------------------
+# BASELINE config 4: synthetic nonsymmetric CSR with power-law row lengths, generated
+# shard by shard with a counter-based hash so that ANY block of rows can be regenerated
+# bit-identically on any rank (or on the host at small n for partition checks).
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def _mix(x):
+    """splitmix64 finaliser on uint64 arrays (wrap-around arithmetic)."""
+    with np.errstate(over="ignore"):
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return x ^ (x >> np.uint64(31))
+
+
+def _unit(h):
+    """uint64 hash -> float64 in [0, 1)."""
+    return (h >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+
+
+POWERLAW_TOP = 16          # rows carrying the separated leading eigenvalues
+
+
+def powerlaw_rows(n, row0, row1, *, seed=0, band=4096, far_prob=1.0 / 32.0, lmin=4, lmax=2048,
+                  alpha=1.35, chunk=1 << 20):
+    """Rows [row0, row1) of the n x n synthetic operator, as a ``RowBlock`` (global columns).
+
+    * row length  L_r = clip(floor(lmin * u^(-1/alpha)), lmin, lmax): Pareto, mean ~ 15
+    * entry 0 is the diagonal; entry k > 0 sits at column (r + off) mod n with off uniform in
+      [-band, band] (probability 1 - far_prob) or uniform over all columns (far_prob): a local
+      band plus a sparse long-range tail.  Columns inside a row are NOT sorted and may repeat
+      (scipy's csr_matvec and the device SpMV both sum entries in stored order).
+    * off-diagonal values U(-1, 1) * 0.5 / L_r (row sums < 0.5); diagonal 1 + r/n except
+      POWERLAW_TOP rows spread over the matrix whose diagonal is 3.0 + 0.25 i: the wanted
+      largest-real-part eigenvalues are separated, so the solve converges in a few restarts.
+    """
+    from .distributed import RowBlock
+    s0 = np.uint64(seed) * np.uint64(0x9E3779B97F4A7C15)
+    ptr_parts, idx_parts, val_parts = [np.zeros(1, np.int64)], [], []
+    total = 0
+    top_rows = (np.arange(POWERLAW_TOP, dtype=np.int64) * (n // POWERLAW_TOP) + n // (2 * POWERLAW_TOP))
+    for c0 in range(row0, row1, chunk):
+        c1 = min(c0 + chunk, row1)
+        r = np.arange(c0, c1, dtype=np.uint64)
+        with np.errstate(over="ignore"):
+            hr = _mix(r * np.uint64(0xD1342543DE82EF95) + s0)
+        u = 1.0 - _unit(hr)                                   # (0, 1]
+        L = np.clip(np.floor(lmin * u ** (-1.0 / alpha)), lmin, lmax).astype(np.int64)
+        L = np.minimum(L, n)
+        starts = np.concatenate(([0], np.cumsum(L)))
+        nnz = int(starts[-1])
+        row_of = np.repeat(np.arange(c1 - c0, dtype=np.int64), L)
+        k = np.arange(nnz, dtype=np.int64) - starts[row_of]
+        rr = r[row_of]
+        with np.errstate(over="ignore"):
+            h1 = _mix(hr[row_of] + k.astype(np.uint64) * np.uint64(0x2545F4914F6CDD1D))
+            h2 = _mix(h1 + np.uint64(0x632BE59BD9B4E019))
+            h3 = _mix(h2 + np.uint64(0x9E3779B97F4A7C15))
+        far = _unit(h2) < far_prob
+        off = (h1 % np.uint64(2 * band + 1)).astype(np.int64) - band
+        col = np.where(far, (h1 % np.uint64(n)).astype(np.int64),
+                       (rr.astype(np.int64) + off) % n)
+        val = (2.0 * _unit(h3) - 1.0) * (0.5 / L[row_of])
+        diag = k == 0
+        col[diag] = rr[diag].astype(np.int64)
+        dval = 1.0 + rr[diag].astype(np.float64) / n
+        is_top = np.isin(rr[diag].astype(np.int64), top_rows)
+        if is_top.any():
+            which = np.searchsorted(top_rows, rr[diag].astype(np.int64)[is_top])
+            dval[is_top] = 3.0 + 0.25 * which
+        val[diag] = dval
+        idx_parts.append(col.astype(np.int32 if n < 2**31 else np.int64))
+        val_parts.append(val)
+        ptr_parts.append(starts[1:] + total)
+        total += nnz
+    indptr = np.concatenate(ptr_parts)
+    if total < 2**31 - 1:
+        indptr = indptr.astype(np.int32)
+    return RowBlock(indptr, np.concatenate(idx_parts), np.concatenate(val_parts), row0, (n, n))
+
+
+def powerlaw(n, **kw):
+    """The whole operator as a scipy CSR matrix (small n: tests, single-GPU runs)."""
+    b = powerlaw_rows(n, 0, n, **kw)
+    return sp.csr_matrix((b.data, b.indices, b.indptr), shape=(n, n))

@@ -52,6 +52,7 @@ struct SpmvArgs {
   int64_t n_local_cols;    // column ids below this are local
   int nblocks;
   int tile;                // nnz staged per block iteration
+  int threads;             // block size: 128 or 256
   const StepCtl* ctl;      // nullptr for the stand-alone entry point
 };
 

@@ -91,6 +91,7 @@ struct ab200_solver {
   int64_t* rowblk = nullptr;
   int nblk = 0;
   int tile = 0;
+  int spmv_threads = 256;
   cplx* ghost = nullptr;
   int64_t n_local_cols = 0;
 
@@ -111,7 +112,7 @@ struct ab200_solver {
 
   // options
   int opt_grid_mult = 0, opt_restart_variant = 0, opt_ortho_variant = 0, opt_spmv_tile = 0,
-      opt_fused_ct = 0;
+      opt_fused_ct = 0, opt_spmv_threads = 0;
 
   // stats
   bool timing = false;
@@ -445,15 +446,17 @@ int ab200_set_csr(ab200_solver* s, const void* indptr, int indptr_bits, const in
                        s->stream));
     CU(cudaMemcpyAsync(s->values, values, vb * (size_t)nnz, cudaMemcpyHostToDevice, s->stream));
   }
-  // nnz tile: about one row per thread of a 256-thread block, within [512, 2048]
+  // nnz tile: about one row per thread of the block, within [512, 2048]
+  const int threads = s->opt_spmv_threads == 128 ? 128 : 256;
   int tile = s->opt_spmv_tile;
   if (tile <= 0) {
     double avg = (double)nnz / (double)s->n;
-    tile = (int)(avg * 256.0);
-    tile = (tile + 255) / 256 * 256;
+    tile = (int)(avg * threads);
+    tile = (tile + 127) / 128 * 128;
     if (tile < 512) tile = 512;
     if (tile > 2048) tile = 2048;
   }
+  s->spmv_threads = threads;
   int64_t nblk = (nnz + tile - 1) / tile;
   if (nblk < 1) nblk = 1;
   REQUIRE(nblk < (1ll << 30), "too many SpMV tiles");
@@ -516,6 +519,7 @@ static int enqueue_spmv(ab200_solver* s, const cplx* x, cplx* y, const double* x
   a.n_local_cols = s->n_local_cols;
   a.nblocks = s->nblk;
   a.tile = s->tile;
+  a.threads = s->spmv_threads;
   a.ctl = in_expand ? s->ctl : nullptr;
   const double sv = s->value_kind == AB200_F64 ? 8.0 : 16.0;
   const double bytes = (double)s->nnz * (sv + 4.0) + (double)s->n * (s->indptr_bits / 8 + 32.0) +
@@ -866,6 +870,8 @@ int ab200_set_option(ab200_solver* s, const char* key, int64_t value) {
     s->opt_ortho_variant = (int)value;
   else if (!strcmp(key, "fused_ct"))
     s->opt_fused_ct = (int)value;
+  else if (!strcmp(key, "spmv_threads"))
+    s->opt_spmv_threads = (int)value;
   else if (!strcmp(key, "spmv_tile"))
     s->opt_spmv_tile = (int)value;
   else

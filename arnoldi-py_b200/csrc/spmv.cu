@@ -20,7 +20,6 @@
 
 namespace ab200 {
 
-constexpr int kSpmvThreads = 256;
 constexpr int kLongRow = 96;
 constexpr int kMaxLongPerTile = 64;
 
@@ -67,7 +66,7 @@ __global__ void spmv_plan_kernel(const IdxT* __restrict__ indptr, int64_t n, int
   rowblk[b] = lo;
 }
 
-template <typename IdxT, typename ValT>
+template <typename IdxT, typename ValT, int kSpmvThreads>
 __global__ void __launch_bounds__(kSpmvThreads) spmv_tile_kernel(SpmvArgs a) {
   if (a.ctl != nullptr && a.ctl->stop) return;
 
@@ -197,18 +196,23 @@ cudaError_t launch_spmv_plan(const void* indptr, int indptr_bits, int64_t n, int
   return cudaGetLastError();
 }
 
-template <typename IdxT, typename ValT>
-static cudaError_t launch_spmv_t(const SpmvArgs& a, cudaStream_t st) {
+template <typename IdxT, typename ValT, int THREADS>
+static cudaError_t launch_spmv_tt(const SpmvArgs& a, cudaStream_t st) {
   const size_t smem = (size_t)(a.tile + 4) * (sizeof(ValT) + sizeof(int32_t));
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(spmv_tile_kernel<IdxT, ValT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         96 * 1024);
+    cudaFuncSetAttribute(spmv_tile_kernel<IdxT, ValT, THREADS>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     attr_done = true;
   }
   const int grid = a.nblocks;  // one tile per block; blocks are small and many per SM
-  spmv_tile_kernel<IdxT, ValT><<<grid, kSpmvThreads, smem, st>>>(a);
+  spmv_tile_kernel<IdxT, ValT, THREADS><<<grid, THREADS, smem, st>>>(a);
   return cudaGetLastError();
+}
+template <typename IdxT, typename ValT>
+static cudaError_t launch_spmv_t(const SpmvArgs& a, cudaStream_t st) {
+  return a.threads == 128 ? launch_spmv_tt<IdxT, ValT, 128>(a, st)
+                          : launch_spmv_tt<IdxT, ValT, 256>(a, st);
 }
 
 cudaError_t launch_spmv(const SpmvArgs& a, int indptr_bits, int value_kind, cudaStream_t st) {

@@ -170,7 +170,8 @@ int ab200_timer_stop(ab200_solver *s, double *elapsed_ms);
  *   "fused_ct"        column-tile width of the fused sweep (1..8)
  *   "restart_variant" outputs per warp of the restart kernel (4, 8, 16)
  *   "grid_mult"       resident blocks per SM for the orthogonalisation kernels
- *   "spmv_tile"       non-zeros staged per SpMV block (takes effect at the next ab200_set_csr) */
+ *   "spmv_tile"       non-zeros staged per SpMV block    } take effect at the next
+ *   "spmv_threads"    SpMV block size, 128 or 256        } ab200_set_csr */
 int ab200_set_option(ab200_solver *s, const char *key, int64_t value);
 
 /* Pinned host memory for callers that want asynchronous, full-speed uploads. */

@@ -180,3 +180,26 @@ def test_partial_schur_vs_oracle_medium(gpu):
     assert (np.linalg.norm(A @ X - X * w, axis=0) / np.abs(w)).max() <= 1e-6
     # DGKS behaviour: the Laplacian fires the second round on (nearly) every step
     assert stats["second_rounds"] >= 0.9 * cnt["rounds"] / 2 - 5
+
+
+def test_partial_schur_powerlaw_vs_oracle(gpu):
+    """Config-4 operator family at small n: skewed rows (carried / tree-reduced segments in
+    the SpMV), unsorted columns, nonsymmetric; same seed through the oracle."""
+    from arnoldi_b200 import partial_schur
+    from arnoldi_b200.matrices import powerlaw
+    from arnoldi_b200.utils import arg_largest_real
+    A = powerlaw(60000)
+    kw = dict(max_dim=40, stopping_criterion=1e-8, max_restarts=200)
+    np.random.seed(0)
+    stats = {}
+    Q, T, hist = partial_schur(A, 10, sort_function=arg_largest_real, stats=stats, **kw)
+    np.random.seed(0)
+    Qo, To, histo = oracle.partial_schur(A, 10, sort_function=oracle.arg_largest_real, **kw)
+    rel = np.abs(np.diag(T) - np.diag(To)) / np.abs(np.diag(To))
+    assert rel.max() <= RITZ_RTOL, rel
+    assert int(hist.restarts[0]) == int(histo.restarts[0])
+    w, S = np.linalg.eig(T)
+    X = Q @ S
+    assert (np.linalg.norm(A @ X - X * w, axis=0) / np.abs(w)).max() <= 1e-8
+    np.testing.assert_allclose(np.sort(np.diag(T).real)[::-1],
+                               6.75 - 0.25 * np.arange(10), atol=1e-3)

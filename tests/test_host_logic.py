@@ -118,3 +118,25 @@ def test_history_and_argument_checks():
         partial_schur(A[:, :10], 3)
     with pytest.raises(AssertionError):
         partial_schur(A, 3, ortho="householder")
+
+
+def test_powerlaw_generator_is_shardable():
+    """Config-4 operator: any block of rows regenerates bit-identically, whatever the chunking."""
+    from arnoldi_b200.matrices import POWERLAW_TOP, powerlaw, powerlaw_rows
+    n = 30000
+    A = powerlaw(n)
+    lens = np.diff(A.indptr)
+    assert lens.min() >= 4 and lens.max() <= 2048 and 8 < lens.mean() < 25
+    assert lens.max() > 20 * np.median(lens)            # skewed rows
+    for r0, r1, chunk in ((0, n, 1 << 20), (123, 20011, 4096), (29990, n, 7)):
+        b = powerlaw_rows(n, r0, r1, chunk=chunk)
+        S = A[r0:r1]
+        np.testing.assert_array_equal(b.indptr, S.indptr)
+        np.testing.assert_array_equal(b.indices, S.indices)
+        np.testing.assert_array_equal(b.data, S.data)
+    # nonsymmetric, diagonal first in every row, separated leading diagonal entries
+    assert (A != A.T).nnz > 0
+    np.testing.assert_array_equal(A.indices[A.indptr[:-1]], np.arange(n))
+    d = np.sort(A.diagonal())[::-1]
+    np.testing.assert_allclose(d[:POWERLAW_TOP], 3.0 + 0.25 * np.arange(POWERLAW_TOP)[::-1])
+    assert d[POWERLAW_TOP] <= 2.0

@@ -68,8 +68,9 @@ def main():
         opts = dict(kv.split("=") for kv in spec.split(",") if kv)
         for k in ("ortho_variant", "fused_ct", "grid_mult", "restart_variant"):
             dev.set_option(k, int(opts.get(k, 0)))
-        if "spmv_tile" in opts:
-            dev.set_option("spmv_tile", int(opts["spmv_tile"]))
+        if "spmv_tile" in opts or "spmv_threads" in opts:
+            dev.set_option("spmv_tile", int(opts.get("spmv_tile", 0)))
+            dev.set_option("spmv_threads", int(opts.get("spmv_threads", 0)))
             dev.set_csr(A.indptr, A.indices, A.data)
         cycle()
         dev.reset_stats()
