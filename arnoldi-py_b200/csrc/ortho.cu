@@ -369,7 +369,7 @@ __device__ __forceinline__ void cp_async_wait() {
 // no registers held) while the current one is processed, so requests stay in flight across
 // the block barrier.  PF = false: plain register loads (more blocks per SM instead).
 template <int CT, int R, bool PF>
-__global__ void __launch_bounds__(CT < 8 ? 256 : 512) cgs_fused_kernel(OrthoArgs a) {
+__global__ void __launch_bounds__(CT < 5 ? 256 : 512) cgs_fused_kernel(OrthoArgs a) {
   StepCtl* ctl = a.ctl;
   if (ctl->stop) return;
 
@@ -762,23 +762,29 @@ cudaError_t launch_cgs_fused(const OrthoArgs& a, int num_sms, cudaStream_t st, i
                              int variant, int fused_ct) {
   int ct, warps;
   pass1_shape(a.ncols, &ct, &warps);
-  if (ct < 5 && a.ncols >= 20) {  // measured: 5-column tiles (fewer partial sums to exchange)
-    ct = 5;
-    warps = (a.ncols + 4) / 5;
+  if (a.ncols >= 20) {
+    // measured: 5-column tiles are the sweet spot (fewer partial sums to exchange than with
+    // narrower tiles, fewer registers than with wider ones); up to 16 warps per block
+    ct = a.ncols <= 80 ? 5 : (a.ncols + 15) / 16;
+    warps = (a.ncols + ct - 1) / ct;
   }
   if (fused_ct > 0 && fused_ct <= 8) {
     const int wf = (a.ncols + fused_ct - 1) / fused_ct;
-    if (wf <= (fused_ct < 8 ? 8 : 16)) ct = fused_ct, warps = wf;
+    if (wf <= (fused_ct < 5 ? 8 : 16)) ct = fused_ct, warps = wf;
   }
   if (warps > 16) return cudaErrorInvalidValue;
-  if (variant != 2) {
+  // cp.async staging needs 2 x warps x CT x R x 512 B of shared memory: keep it to shapes that
+  // still leave two blocks per SM
+  const int rr = ct <= 5 ? 2 : 1;
+  const size_t stage_bytes = (size_t)2 * warps * ct * rr * kWarp * sizeof(cplx);
+  if (variant != 2 && stage_bytes <= 96 * 1024) {
     switch (ct) {
       case 1: return launch_fused_t<1, 2, true>(a, warps, num_sms, st, grid_mult);
       case 2: return launch_fused_t<2, 2, true>(a, warps, num_sms, st, grid_mult);
       case 3: return launch_fused_t<3, 2, true>(a, warps, num_sms, st, grid_mult);
       case 4: return launch_fused_t<4, 2, true>(a, warps, num_sms, st, grid_mult);
       case 5: return launch_fused_t<5, 2, true>(a, warps, num_sms, st, grid_mult);
-      case 6: return launch_fused_t<6, 2, true>(a, warps, num_sms, st, grid_mult);
+      case 6: return launch_fused_t<6, 1, true>(a, warps, num_sms, st, grid_mult);
       case 7: return launch_fused_t<7, 1, true>(a, warps, num_sms, st, grid_mult);
       default: return launch_fused_t<8, 1, true>(a, warps, num_sms, st, grid_mult);
     }
@@ -789,7 +795,7 @@ cudaError_t launch_cgs_fused(const OrthoArgs& a, int num_sms, cudaStream_t st, i
     case 3: return launch_fused_t<3, 2, false>(a, warps, num_sms, st, grid_mult);
     case 4: return launch_fused_t<4, 2, false>(a, warps, num_sms, st, grid_mult);
     case 5: return launch_fused_t<5, 2, false>(a, warps, num_sms, st, grid_mult);
-    case 6: return launch_fused_t<6, 2, false>(a, warps, num_sms, st, grid_mult);
+    case 6: return launch_fused_t<6, 1, false>(a, warps, num_sms, st, grid_mult);
     case 7: return launch_fused_t<7, 1, false>(a, warps, num_sms, st, grid_mult);
     default: return launch_fused_t<8, 1, false>(a, warps, num_sms, st, grid_mult);
   }

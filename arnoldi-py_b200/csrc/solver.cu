@@ -91,7 +91,7 @@ struct ab200_solver {
   int64_t* rowblk = nullptr;
   int nblk = 0;
   int tile = 0;
-  int spmv_threads = 256;
+  int spmv_threads = 128;
   cplx* ghost = nullptr;
   int64_t n_local_cols = 0;
 
@@ -447,7 +447,7 @@ int ab200_set_csr(ab200_solver* s, const void* indptr, int indptr_bits, const in
     CU(cudaMemcpyAsync(s->values, values, vb * (size_t)nnz, cudaMemcpyHostToDevice, s->stream));
   }
   // nnz tile: about one row per thread of the block, within [512, 2048]
-  const int threads = s->opt_spmv_threads == 128 ? 128 : 256;
+  const int threads = s->opt_spmv_threads == 256 ? 256 : 128;  // 128 measured 3% faster
   int tile = s->opt_spmv_tile;
   if (tile <= 0) {
     double avg = (double)nnz / (double)s->n;
@@ -460,7 +460,7 @@ int ab200_set_csr(ab200_solver* s, const void* indptr, int indptr_bits, const in
   int64_t nblk = (nnz + tile - 1) / tile;
   if (nblk < 1) nblk = 1;
   REQUIRE(nblk < (1ll << 30), "too many SpMV tiles");
-  CU(cudaMalloc(&s->rowblk, sizeof(int64_t) * (size_t)(nblk + 1)));
+  CU(cudaMalloc(&s->rowblk, sizeof(int64_t) * 2 * (size_t)(nblk + 1)));
   CU(launch_spmv_plan(s->indptr, indptr_bits, s->n, nnz, tile, (int)nblk, s->rowblk, s->stream));
   CU(cudaStreamSynchronize(s->stream));
   s->indptr_bits = indptr_bits;

@@ -47,10 +47,14 @@ __device__ __forceinline__ cplx cadd_rn(cplx a, cplx b) {
 template <typename IdxT>
 __global__ void spmv_plan_kernel(const IdxT* __restrict__ indptr, int64_t n, int64_t nnz, int tile,
                                  int nblocks, int64_t* __restrict__ rowblk) {
+  // rowblk[b] = first row of tile b; rowblk[nblocks + 1 + b] = indptr of that row, so a block
+  // reads its row range AND its nnz range with independent loads (no dependent round trip)
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b > nblocks) return;
+  int64_t* __restrict__ nnzblk = rowblk + nblocks + 1;
   if (b == nblocks) {
     rowblk[b] = n;
+    nnzblk[b] = nnz;
     return;
   }
   const int64_t target = (int64_t)b * tile;
@@ -64,6 +68,7 @@ __global__ void spmv_plan_kernel(const IdxT* __restrict__ indptr, int64_t n, int
       hi = mid;
   }
   rowblk[b] = lo;
+  nnzblk[b] = (int64_t)indptr[lo];
 }
 
 template <typename IdxT, typename ValT, int kSpmvThreads>
@@ -87,10 +92,17 @@ __global__ void __launch_bounds__(kSpmvThreads) spmv_tile_kernel(SpmvArgs a) {
   const int tid = threadIdx.x;
   const int tile = a.tile;
 
+  const int64_t* __restrict__ nnzblk = a.rowblk + a.nblocks + 1;
   for (int b = blockIdx.x; b < a.nblocks; b += gridDim.x) {
     const int64_t r0 = a.rowblk[b], r1 = a.rowblk[b + 1];
     if (r0 >= r1) continue;
-    const int64_t s = (int64_t)indptr[r0], e = (int64_t)indptr[r1];
+    const int64_t s = nnzblk[b], e = nnzblk[b + 1];
+    // this thread's first row: fetch its extent now, overlapped with the staging loads
+    int64_t rs0 = 0, re0 = 0;
+    if (r0 + tid < r1) {
+      rs0 = (int64_t)indptr[r0 + tid];
+      re0 = (int64_t)indptr[r0 + tid + 1];
+    }
     // at least one iteration so that empty rows get y = 0
     for (int64_t cs = s; cs == s || cs < e; cs += tile) {
       const int64_t ce = (cs + tile < e) ? cs + tile : e;
@@ -120,7 +132,9 @@ __global__ void __launch_bounds__(kSpmvThreads) spmv_tile_kernel(SpmvArgs a) {
       __syncthreads();
       // ---- one thread per row, stored order
       for (int64_t row = r0 + tid; row < r1; row += kSpmvThreads) {
-        const int64_t rs = (int64_t)indptr[row], re = (int64_t)indptr[row + 1];
+        const bool first = (row == r0 + tid);
+        const int64_t rs = first ? rs0 : (int64_t)indptr[row];
+        const int64_t re = first ? re0 : (int64_t)indptr[row + 1];
         if (re <= cs && !(rs == re && cs == s)) continue;  // finished in an earlier tile
         if (rs >= ce && rs != re) continue;                // starts in a later tile
         const int64_t lo = rs > cs ? rs : cs;
