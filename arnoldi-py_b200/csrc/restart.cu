@@ -62,20 +62,9 @@ __global__ void __launch_bounds__(512) restart_kernel(RestartArgs a) {
       for (int t = 0; t < B; ++t) {
         if (i + t < m) {
           const int qo = (i + t) * p + k0;
-          // four sweeps over the outputs so that back-to-back DFMAs are independent
-          cplx qv[PT];
 #pragma unroll
           for (int k = 0; k < PT; ++k)
-            qv[k] = (k < nk) ? (QS ? sq_s[qo + k] : __ldg(sq_g + qo + k)) : make_double2(0.0, 0.0);
-          const cplx u = cur[t];
-#pragma unroll
-          for (int k = 0; k < PT; ++k) acc[k].x = fma(u.x, qv[k].x, acc[k].x);
-#pragma unroll
-          for (int k = 0; k < PT; ++k) acc[k].y = fma(u.x, qv[k].y, acc[k].y);
-#pragma unroll
-          for (int k = 0; k < PT; ++k) acc[k].x = fma(-u.y, qv[k].y, acc[k].x);
-#pragma unroll
-          for (int k = 0; k < PT; ++k) acc[k].y = fma(u.y, qv[k].x, acc[k].y);
+            if (k < nk) cfma(acc[k], cur[t], QS ? sq_s[qo + k] : __ldg(sq_g + qo + k));
         }
       }
 #pragma unroll

@@ -97,12 +97,6 @@ __global__ void __launch_bounds__(kSpmvThreads) spmv_tile_kernel(SpmvArgs a) {
     const int64_t r0 = a.rowblk[b], r1 = a.rowblk[b + 1];
     if (r0 >= r1) continue;
     const int64_t s = nnzblk[b], e = nnzblk[b + 1];
-    // this thread's first row: fetch its extent now, overlapped with the staging loads
-    int64_t rs0 = 0, re0 = 0;
-    if (r0 + tid < r1) {
-      rs0 = (int64_t)indptr[r0 + tid];
-      re0 = (int64_t)indptr[r0 + tid + 1];
-    }
     // at least one iteration so that empty rows get y = 0
     for (int64_t cs = s; cs == s || cs < e; cs += tile) {
       const int64_t ce = (cs + tile < e) ? cs + tile : e;
@@ -132,9 +126,7 @@ __global__ void __launch_bounds__(kSpmvThreads) spmv_tile_kernel(SpmvArgs a) {
       __syncthreads();
       // ---- one thread per row, stored order
       for (int64_t row = r0 + tid; row < r1; row += kSpmvThreads) {
-        const bool first = (row == r0 + tid);
-        const int64_t rs = first ? rs0 : (int64_t)indptr[row];
-        const int64_t re = first ? re0 : (int64_t)indptr[row + 1];
+        const int64_t rs = (int64_t)indptr[row], re = (int64_t)indptr[row + 1];
         if (re <= cs && !(rs == re && cs == s)) continue;  // finished in an earlier tile
         if (rs >= ce && rs != re) continue;                // starts in a later tile
         const int64_t lo = rs > cs ? rs : cs;
