@@ -123,8 +123,8 @@ def partial_schur(
             v0 = rand_normalized_vector(n, np.complex128)
         lap("host_v0")
         dev.set_columns(0, v0[r0:r1])
-        if multi:
-            comm.barrier()   # every rank's column 0 is in place before any halo read
+        # (multi-GPU: ab200_expand opens with a device-side peer barrier, so every rank's
+        #  columns are in place before any halo read -- no host barrier needed here)
 
         def grow(start):
             cols, n_iter, _ = dev.expand(start, max_dim, tol, ortho=kind)
@@ -152,8 +152,6 @@ def partial_schur(
             lap("host_schur")
             # truncate
             dev.restart(Q, m, p)
-            if multi:
-                comm.barrier()   # peers read column p of this rank's block in the next SpMV
             lap("restart")
             H[:p, :p] = T2[:p, :p]
             H[p, :p] = spike

@@ -38,6 +38,8 @@ cudaError_t launch_cgs_pass2(const OrthoArgs& a, int num_sms, cudaStream_t st, i
 cudaError_t launch_mgs_step(const OrthoArgs& a, int i, int num_sms, cudaStream_t st,
                             int grid_mult);
 
+cudaError_t launch_peer_barrier(const PeerComm& pc, StepCtl* ctl, cudaStream_t st);
+
 // ---------------------------------------------------------------- SpMV
 struct SpmvArgs {
   const void* indptr;      // [n + 1], 32- or 64-bit, relative to the local block

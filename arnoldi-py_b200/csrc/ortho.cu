@@ -661,6 +661,23 @@ __global__ void __launch_bounds__(256) mgs_step_kernel(OrthoArgs a, int i) {
   }
 }
 
+// ------------------------------------------------------------------ peer barrier
+// All ranks' streams meet here: everything a rank enqueued before this kernel (restart
+// update, column uploads) is complete and visible before any rank runs what follows (the
+// first halo gather of an expansion).  One 32-thread block, one NVLink round trip.
+__global__ void peer_barrier_kernel(PeerComm pc, StepCtl* ctl) {
+  __shared__ double token[1];
+  if (threadIdx.x == 0) token[0] = 1.0;
+  __syncthreads();
+  __threadfence_system();
+  peer_allreduce(pc, token, 1, ctl);
+}
+cudaError_t launch_peer_barrier(const PeerComm& pc, StepCtl* ctl, cudaStream_t st) {
+  if (pc.nranks <= 1) return cudaSuccess;
+  peer_barrier_kernel<<<1, 32, 0, st>>>(pc, ctl);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ launchers
 static int pick_grid(int64_t work_items, int blocks_per_sm, int num_sms, int cap) {
   int64_t g = (int64_t)num_sms * blocks_per_sm;

@@ -561,6 +561,11 @@ int ab200_expand(ab200_solver* s, int start_dim, int end_dim, double tol, double
   init_ctl_kernel<<<1, 32, 0, s->stream>>>(s->ctl, nullptr, 0, false);
   CU(cudaGetLastError());
   s->st.kernel_launches += 1;
+  if (s->nranks > 1) {
+    // every rank's basis (restart update / uploaded columns) is final before any halo read
+    CU(launch_peer_barrier(s->comm, s->ctl, s->stream));
+    s->st.kernel_launches += 1;
+  }
   for (int j = start_dim; j < end_dim; ++j) {
     cplx* x = s->V + (size_t)j * s->ld;
     cplx* w = s->V + (size_t)(j + 1) * s->ld;

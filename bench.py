@@ -389,8 +389,9 @@ def run_b200_multi(args, rank, world, local):
     from arnoldi_b200.solver import DeviceSolver
     from arnoldi_b200.utils import arg_largest_real, ordered_schur, rand_normalized_vector
 
+    os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl")
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     comm = TorchComm()
     grid = args.grid
     A = lap2d(grid)
@@ -408,7 +409,6 @@ def run_b200_multi(args, rank, world, local):
     dev.set_halo(plan.ghost_cols)
     dev.set_csr(plan.indptr, plan.indices, plan.data)
     dev.set_columns(0, v0[r0:r1])
-    comm.barrier()
 
     def grow(start):
         cols, n_iter, brk = dev.expand(start, MAX_DIM, TOL)
@@ -423,7 +423,6 @@ def run_b200_multi(args, rank, world, local):
         Q = Q1 @ Q2
         spike = H[m, :m] @ Q[:, :P]
         dev.restart(Q, m, P)
-        comm.barrier()
         H[:P, :P] = T2[:P, :P]
         H[P, :P] = spike
         H[P, P:] = 0
