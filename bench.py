@@ -311,7 +311,9 @@ def run_b200(args):
                    "share_of_step": v["ms"] / ms} for k, v in classes.items()}
     roofline = {"bound": "hbm", "kernel": top, "achieved": classes[top]["gbs"], "peak": peak,
                 "unit": "GB/s", "frac": classes[top]["gbs"] / peak, "peak_source": peak_src,
-                "traffic": traffic_from_profile(top, grid), "kernels": kernels,
+                "traffic": traffic_from_profile(top, grid, classes[top]["bytes"] / classes[top]["launches"]),
+                "algorithmic_bytes_per_launch": classes[top]["bytes"] / classes[top]["launches"],
+                "kernels": kernels,
                 "dgks_second_round_fraction": st["second_rounds"] / max(1, st["arnoldi_steps"])}
     dev.close()
 
@@ -361,14 +363,17 @@ def run_b200(args):
     print(json.dumps(line))
 
 
-def traffic_from_profile(kernel, grid):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture
-    (profiles/traffic.json, written from `ncu --set full`), or None."""
+def traffic_from_profile(kernel, grid, bytes_per_launch=None):
+    """DRAM bytes per launch of the dominant kernel, from the committed `ncu --set full`
+    capture (profiles/traffic.json: measured DRAM bytes / algorithmic bytes of one launch)
+    scaled to the average launch of this run; None when no capture covers the kernel."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             t = json.load(f)
         ent = t.get(f"{kernel}@lap2d({grid})")
-        return ent
+        if ent is None or bytes_per_launch is None:
+            return None
+        return float(ent["ratio"]) * float(bytes_per_launch)
     except Exception:
         return None
 
