@@ -381,7 +381,8 @@ __global__ void __launch_bounds__(CT < 5 ? 256 : 512) cgs_fused_kernel(OrthoArgs
   const int c = a.ncols;
   cplx* spart = reinterpret_cast<cplx*>(fused_smem);  // [2][nwarps][ROWS]
   cplx* scoef = spart + 2 * nwarps * ROWS;            // [nwarps * CT]
-  cplx* sw = scoef + nwarps * CT;                     // PF: [2][ROWS]           chunk of w
+  cplx* swp = scoef + nwarps * CT;                    // [ROWS]                  w' of the chunk
+  cplx* sw = swp + ROWS;                              // PF: [2][ROWS]           chunk of w
   cplx* sv = sw + 2 * ROWS;                           // PF: [2][nwarps][CT][ROWS] chunk of U
   for (int i = threadIdx.x; i < nwarps * CT; i += blockDim.x)
     scoef[i] = i < c ? a.coef[i] : make_double2(0.0, 0.0);
@@ -436,7 +437,8 @@ __global__ void __launch_bounds__(CT < 5 ? 256 : 512) cgs_fused_kernel(OrthoArgs
     }
     cp_async_commit();
   }
-  for (int64_t q = blockIdx.x; q < nchunks; q += gridDim.x, buf ^= 1) {
+  unsigned iter = 0;
+  for (int64_t q = blockIdx.x; q < nchunks; q += gridDim.x, buf ^= 1, ++iter) {
     const int64_t base = q * ROWS + lane;
     const bool full = q * ROWS + ROWS <= a.n;
     const int64_t qn = q + gridDim.x;
@@ -483,25 +485,22 @@ __global__ void __launch_bounds__(CT < 5 ? 256 : 512) cgs_fused_kernel(OrthoArgs
       mine[r * kWarp + lane] = t;
     }
     __syncthreads();  // partial sums (and, PF, warp 0's chunk of w) visible to the block
-    if (PF) {
+    // ONE warp (rotating with the chunk, so the work spreads evenly) rebuilds w' for the
+    // chunk, stores it and publishes it through shared memory; the others only read it back.
+    // (Every warp doing the W-term sum itself saturated the shared-memory pipe.)
+    if (warp == (int)(iter % nwarps)) {
+      if (PF) {
 #pragma unroll
-      for (int r = 0; r < R; ++r) wv[r] = sw[(size_t)buf * ROWS + r * kWarp + lane];
-      // every warp is past its reads of sw[buf ^ 1] (previous chunk): refill it
-      if (warp == 0 && qn < nchunks) stage_w(qn, buf ^ 1);
-      cp_async_commit();
-    }
-    // every warp rebuilds w' for the chunk (same order everywhere: bit-identical copies)
-    const cplx* all = spart + (size_t)buf * nwarps * ROWS;
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      cplx t = make_double2(0.0, 0.0);
-      for (int k2 = 0; k2 < nwarps; ++k2) t = cadd(t, all[k2 * ROWS + r * kWarp + lane]);
-      wv[r].x -= t.x;
-      wv[r].y -= t.y;
-    }
-    if (warp == 0) {
+        for (int r = 0; r < R; ++r) wv[r] = sw[(size_t)buf * ROWS + r * kWarp + lane];
+      }
+      const cplx* all = spart + (size_t)buf * nwarps * ROWS;
 #pragma unroll
       for (int r = 0; r < R; ++r) {
+        cplx t = make_double2(0.0, 0.0);
+        for (int k2 = 0; k2 < nwarps; ++k2) t = cadd(t, all[k2 * ROWS + r * kWarp + lane]);
+        wv[r].x -= t.x;
+        wv[r].y -= t.y;
+        swp[r * kWarp + lane] = wv[r];
         const bool ok = full || base + r * kWarp < a.n;
         if (ok) {
           st_stream(w + base + r * kWarp, wv[r]);
@@ -510,6 +509,14 @@ __global__ void __launch_bounds__(CT < 5 ? 256 : 512) cgs_fused_kernel(OrthoArgs
         }
       }
     }
+    if (PF) {
+      // every warp is past its reads of sw[buf ^ 1] (previous chunk): refill it
+      if (warp == 0 && qn < nchunks) stage_w(qn, buf ^ 1);
+      cp_async_commit();
+    }
+    __syncthreads();  // w' of the chunk is published
+#pragma unroll
+    for (int r = 0; r < R; ++r) wv[r] = swp[r * kWarp + lane];
 #pragma unroll
     for (int k = 0; k < CT; ++k) {
       if (k < mycols) {
@@ -528,9 +535,16 @@ __global__ void __launch_bounds__(CT < 5 ? 256 : 512) cgs_fused_kernel(OrthoArgs
       if (lane == 0) a.part[(size_t)(mycol0 + k) * gcap + blockIdx.x] = s;
     }
   }
-  if (warp == 0) {
+  __shared__ double s_nw[16];
+  {
     double s = warp_sum(nacc);
-    if (lane == 0) a.npart[blockIdx.x] = s;
+    if (lane == 0) s_nw[warp] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int k = 0; k < nwarps; ++k) t += s_nw[k];
+    a.npart[blockIdx.x] = t;
   }
 
   __shared__ int s_last;
@@ -754,7 +768,7 @@ static cudaError_t launch_fused_t(const OrthoArgs& a, int warps, int num_sms, cu
   const int threads = warps * kWarp;
   constexpr int ROWS = kWarp * R;
   const int64_t nchunks = (a.n + ROWS - 1) / ROWS;
-  size_t smem = sizeof(cplx) * ((size_t)2 * warps * ROWS + (size_t)warps * CT);
+  size_t smem = sizeof(cplx) * ((size_t)2 * warps * ROWS + (size_t)warps * CT + ROWS);
   if (PF) smem += sizeof(cplx) * ((size_t)2 * ROWS + (size_t)2 * warps * CT * ROWS);
   const size_t need = sizeof(double) * (2 * a.ncols + 2);
   if (smem < need) smem = need;
