@@ -47,14 +47,10 @@ __device__ __forceinline__ cplx cadd_rn(cplx a, cplx b) {
 template <typename IdxT>
 __global__ void spmv_plan_kernel(const IdxT* __restrict__ indptr, int64_t n, int64_t nnz, int tile,
                                  int nblocks, int64_t* __restrict__ rowblk) {
-  // rowblk[b] = first row of tile b; rowblk[nblocks + 1 + b] = indptr of that row, so a block
-  // reads its row range AND its nnz range with independent loads (no dependent round trip)
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b > nblocks) return;
-  int64_t* __restrict__ nnzblk = rowblk + nblocks + 1;
   if (b == nblocks) {
     rowblk[b] = n;
-    nnzblk[b] = nnz;
     return;
   }
   const int64_t target = (int64_t)b * tile;
@@ -68,7 +64,6 @@ __global__ void spmv_plan_kernel(const IdxT* __restrict__ indptr, int64_t n, int
       hi = mid;
   }
   rowblk[b] = lo;
-  nnzblk[b] = (int64_t)indptr[lo];
 }
 
 template <typename IdxT, typename ValT, int kSpmvThreads>
@@ -92,11 +87,10 @@ __global__ void __launch_bounds__(kSpmvThreads) spmv_tile_kernel(SpmvArgs a) {
   const int tid = threadIdx.x;
   const int tile = a.tile;
 
-  const int64_t* __restrict__ nnzblk = a.rowblk + a.nblocks + 1;
   for (int b = blockIdx.x; b < a.nblocks; b += gridDim.x) {
     const int64_t r0 = a.rowblk[b], r1 = a.rowblk[b + 1];
     if (r0 >= r1) continue;
-    const int64_t s = nnzblk[b], e = nnzblk[b + 1];
+    const int64_t s = (int64_t)indptr[r0], e = (int64_t)indptr[r1];
     // at least one iteration so that empty rows get y = 0
     for (int64_t cs = s; cs == s || cs < e; cs += tile) {
       const int64_t ce = (cs + tile < e) ? cs + tile : e;
