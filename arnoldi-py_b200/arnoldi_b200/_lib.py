@@ -62,6 +62,8 @@ SIGNATURES = {
     "ab200_comm_export": (C.c_int, [_P, _P]),
     "ab200_comm_connect": (C.c_int, [_P, C.c_int, C.c_int, C.c_char_p, _P]),
     "ab200_set_halo": (C.c_int, [_P, _P, C.c_int64]),
+    "ab200_halo_export": (C.c_int, [_P, _P]),
+    "ab200_halo_connect": (C.c_int, [_P, C.c_char_p, _P, _P, _P]),
     "ab200_set_timing": (C.c_int, [_P, C.c_int]),
     "ab200_reset_stats": (C.c_int, [_P]),
     "ab200_get_stats": (C.c_int, [_P, C.POINTER(Stats)]),

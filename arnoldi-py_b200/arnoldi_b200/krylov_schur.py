@@ -43,6 +43,7 @@ def partial_schur(
     A, nev, *, max_dim=None, stopping_criterion=None, max_restarts=100,
     sort_function=None, p=None,
     ortho="cgs2", v0=None, device=0, stats=None, raise_on_no_convergence=True, comm=None,
+    halo="auto",
 ):
     """Partial Schur decomposition ``A Q = Q T`` of the ``nev`` wanted eigenvalues.
 
@@ -59,6 +60,9 @@ def partial_schur(
         scipy CSR matrix (each rank slices its block of rows) or this rank's ``RowBlock``; every
         rank must seed NumPy's global RNG identically (v0 is drawn globally and sliced); the
         returned Q holds this rank's rows only, T and history are identical on all ranks.
+    halo  : "pull" (each rank gathers the remote entries of v it needs straight from peer HBM),
+        "push" (the owner gathers locally and streams them into the peer's buffer) or "auto"
+        (push when some rank's halo has more than 65 536 scattered entries)
 
     Returns ``(Q, T, history)``: Q (n, nev) complex128, T (nev, nev) complex128.
     """
@@ -115,6 +119,11 @@ def partial_schur(
         if multi:
             dev.connect(comm, part)
             dev.set_halo(plan.ghost_cols)
+            assert halo in ("auto", "pull", "push")
+            biggest = max(int.from_bytes(b, "little") for b in comm.all_gather_bytes(
+                int(plan.ghost_cols.shape[0]).to_bytes(8, "little")))
+            if halo == "push" or (halo == "auto" and biggest > 65536):
+                dev.connect_halo_push(comm, part, plan.ghost_cols)
             dev.set_csr(plan.indptr, plan.indices, plan.data)
         else:
             dev.set_csr(indptr, indices, data)

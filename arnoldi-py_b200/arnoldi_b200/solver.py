@@ -131,6 +131,31 @@ class DeviceSolver:
         g = np.ascontiguousarray(ghost_cols, dtype=np.int64)
         _lib.check(self.lib.ab200_set_halo(self._h, _ptr(g), int(g.shape[0])))
 
+    def connect_halo_push(self, comm, partition, ghost_cols):
+        """Switch the halo exchange to owner-side push (scattered halos).  Collective, after
+        ``set_halo`` on every rank: ranks swap their ghost lists, each works out which of its
+        rows every peer reads and where they land in that peer's ghost buffer."""
+        blob = C.create_string_buffer(256)
+        _lib.check(self.lib.ab200_halo_export(self._h, blob))
+        blobs = b"".join(comm.all_gather_bytes(blob.raw))
+        lists = comm.all_gather_bytes(np.ascontiguousarray(ghost_cols, dtype=np.int64).tobytes())
+        r0, r1 = partition.rows(comm.rank)
+        send, ptr, dst = [], [0], []
+        for r in range(comm.world):
+            g = np.frombuffer(lists[r], dtype=np.int64)
+            lo, hi = (0, 0) if r == comm.rank else np.searchsorted(g, [r0, r1])
+            send.append(g[lo:hi] - r0)
+            ptr.append(ptr[-1] + int(hi - lo))
+            dst.append(int(lo))
+        send_idx = np.ascontiguousarray(np.concatenate(send), dtype=np.int64)
+        send_ptr = np.array(ptr, dtype=np.int64)
+        dst_off = np.array(dst, dtype=np.int64)
+        if send_idx.shape[0] == 0:
+            send_idx = np.zeros(1, np.int64)
+        _lib.check(self.lib.ab200_halo_connect(self._h, blobs, _ptr(send_idx), _ptr(send_ptr),
+                                               _ptr(dst_off)))
+        comm.barrier()
+
     # -- measurement ------------------------------------------------------------
     def set_timing(self, on=True):
         _lib.check(self.lib.ab200_set_timing(self._h, int(bool(on))))

@@ -27,6 +27,66 @@ __global__ void __launch_bounds__(256) halo_gather_kernel(HaloArgs a) {
   }
 }
 
+// ---------------------------------------------------------------- owner-side push
+// For scattered halos (power-law operators: millions of isolated remote entries) pulling
+// 16 bytes at a time over NVLink is slow.  The OWNER gathers the entries a peer needs from
+// its own HBM (random local reads at HBM speed) and streams them into the peer's ghost
+// buffer with coalesced remote stores; the last block then raises this rank's "halo k
+// delivered" flag on every peer.  The receiver runs halo_wait_kernel before its SpMV.
+__global__ void __launch_bounds__(256) halo_push_kernel(HaloPushArgs a) {
+  if (a.ctl != nullptr && a.ctl->stop) return;
+  const cplx* __restrict__ src = a.U_col;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < a.nsend;
+       k += (int64_t)gridDim.x * blockDim.x) {
+    int r = 0;
+#pragma unroll
+    for (int q = 1; q < kMaxRanks; ++q)
+      if (q < a.nranks && k >= a.send_ptr[q]) r = q;
+    cplx v = ld_ro(src + a.send_idx[k]);
+    cplx* dst = a.peer_ghost[r] + a.dst_off[r] + (k - a.send_ptr[r]);
+    asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(dst), "d"(v.x), "d"(v.y) : "memory");
+  }
+  __shared__ int s_last;
+  __threadfence_system();
+  if (!last_block_ticket(a.ticket, gridDim.x, &s_last)) return;
+  __threadfence_system();
+  if (threadIdx.x < a.nranks && threadIdx.x != a.rank) {
+    volatile unsigned long long* f = a.peer_hflags[threadIdx.x] + a.rank;
+    *f = a.seq;
+  }
+}
+
+__global__ void halo_wait_kernel(const unsigned long long* hflags, unsigned need_mask,
+                                 unsigned long long seq, StepCtl* ctl) {
+  if (ctl != nullptr && ctl->stop) return;
+  const int q = threadIdx.x;
+  if (q < kMaxRanks && ((need_mask >> q) & 1u)) {
+    volatile const unsigned long long* f = hflags + q;
+    long long spins = 0;
+    while (*f < seq) {
+      if (++spins > (1ll << 26)) {
+        if (ctl) ctl->comm_error = 1;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  __threadfence_system();
+}
+
+cudaError_t launch_halo_push(const HaloPushArgs& a, int num_sms, cudaStream_t st) {
+  int64_t grid = (a.nsend + 255) / 256;
+  if (grid > (int64_t)num_sms * 8) grid = (int64_t)num_sms * 8;
+  if (grid < 1) grid = 1;  // even with nothing to send the flags must be raised
+  halo_push_kernel<<<(int)grid, 256, 0, st>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_halo_wait(const unsigned long long* hflags, unsigned need_mask,
+                             unsigned long long seq, StepCtl* ctl, cudaStream_t st) {
+  halo_wait_kernel<<<1, 32, 0, st>>>(hflags, need_mask, seq, ctl);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_halo_gather(const HaloArgs& a, int num_sms, cudaStream_t st) {
   if (a.nghost <= 0) return cudaSuccess;
   int64_t grid = (a.nghost + 255) / 256;

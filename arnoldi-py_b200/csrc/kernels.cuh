@@ -77,6 +77,23 @@ struct HaloArgs {
 };
 cudaError_t launch_halo_gather(const HaloArgs& a, int num_sms, cudaStream_t st);
 
+struct HaloPushArgs {
+  const cplx* U_col;                      // my column j (un-normalised; the receiver applies scale[j])
+  const int64_t* send_idx;                // [nsend] local row of every entry some peer needs
+  int64_t send_ptr[kMaxRanks + 1];        // entries [send_ptr[r], send_ptr[r+1]) go to rank r
+  int64_t dst_off[kMaxRanks];             // where my block starts in rank r's ghost buffer
+  cplx* peer_ghost[kMaxRanks];            // IPC-mapped ghost buffers
+  unsigned long long* peer_hflags[kMaxRanks];  // IPC-mapped "halo delivered" flags [kMaxRanks]
+  int64_t nsend;
+  unsigned long long seq;
+  unsigned* ticket;
+  int rank, nranks;
+  const StepCtl* ctl;
+};
+cudaError_t launch_halo_push(const HaloPushArgs& a, int num_sms, cudaStream_t st);
+cudaError_t launch_halo_wait(const unsigned long long* hflags, unsigned need_mask,
+                             unsigned long long seq, StepCtl* ctl, cudaStream_t st);
+
 // ---------------------------------------------------------------- restart + helpers
 struct RestartArgs {
   cplx* U;              // basis, updated in place

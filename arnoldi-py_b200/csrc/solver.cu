@@ -109,6 +109,16 @@ struct ab200_solver {
   int64_t* ghost_off = nullptr;            // [nghost] offsets inside the owner's block
   int64_t nghost = 0;
   int64_t seg_start[kMaxRanks + 1] = {0};
+  // owner-side push of the halo
+  bool push = false;
+  unsigned long long* hflags = nullptr;        // my delivery flags [kMaxRanks]
+  unsigned long long hseq = 0;
+  void* peer_ghost[kMaxRanks] = {nullptr};
+  void* peer_hflags[kMaxRanks] = {nullptr};
+  int64_t* send_idx = nullptr;
+  int64_t send_ptr[kMaxRanks + 1] = {0};
+  int64_t dst_off[kMaxRanks] = {0};
+  unsigned* push_ticket = nullptr;
 
   // options
   int opt_grid_mult = 0, opt_restart_variant = 0, opt_ortho_variant = 0, opt_spmv_tile = 0,
@@ -333,6 +343,11 @@ int ab200_destroy(ab200_solver* s) {
     if (s->peer_flags[r]) cudaIpcCloseMemHandle(s->peer_flags[r]);
   }
   cudaFree(s->slots), cudaFree(s->flags), cudaFree(s->seq);
+  for (int r = 0; r < kMaxRanks; ++r) {
+    if (s->peer_ghost[r]) cudaIpcCloseMemHandle(s->peer_ghost[r]);
+    if (s->peer_hflags[r]) cudaIpcCloseMemHandle(s->peer_hflags[r]);
+  }
+  cudaFree(s->hflags), cudaFree(s->send_idx), cudaFree(s->push_ticket);
   cudaFreeHost(s->h_H), cudaFreeHost(s->h_scale), cudaFreeHost(s->h_ctl);
   cudaFreeHost(s->h_step_round2), cudaFreeHost(s->h_q);
   if (s->stream) cudaStreamDestroy(s->stream);
@@ -525,7 +540,30 @@ static int enqueue_spmv(ab200_solver* s, const cplx* x, cplx* y, const double* x
   const double bytes = (double)s->nnz * (sv + 4.0) + (double)s->n * (s->indptr_bits / 8 + 32.0) +
                        32.0 * (double)s->nghost;
   LaunchScope ls(s, K_SPMV, step, 0, bytes);
-  if (s->nghost > 0) {
+  if (s->push) {
+    if (!in_expand) return set_err(AB200_ESTATE, "halo SpMV is only available inside ab200_expand");
+    s->hseq += 1;
+    HaloPushArgs p;
+    p.U_col = x;
+    p.send_idx = s->send_idx;
+    for (int r = 0; r <= kMaxRanks; ++r) p.send_ptr[r] = s->send_ptr[r];
+    unsigned need = 0;
+    for (int r = 0; r < kMaxRanks; ++r) {
+      p.dst_off[r] = s->dst_off[r];
+      p.peer_ghost[r] = static_cast<cplx*>(s->peer_ghost[r]);
+      p.peer_hflags[r] = static_cast<unsigned long long*>(s->peer_hflags[r]);
+      if (r < s->nranks && r != s->rank) need |= 1u << r;
+    }
+    p.nsend = s->send_ptr[s->nranks];
+    p.seq = s->hseq;
+    p.ticket = s->push_ticket;
+    p.rank = s->rank;
+    p.nranks = s->nranks;
+    p.ctl = s->ctl;
+    CU(launch_halo_push(p, s->num_sms, s->stream));
+    CU(launch_halo_wait(s->hflags, need, s->hseq, s->ctl, s->stream));
+    s->st.kernel_launches += 2;
+  } else if (s->nghost > 0) {
     if (!in_expand) return set_err(AB200_ESTATE, "halo SpMV is only available inside ab200_expand");
     HaloArgs h;
     for (int r = 0; r < kMaxRanks; ++r) {
@@ -809,6 +847,76 @@ int ab200_set_halo(ab200_solver* s, const int64_t* ghost_cols, int64_t nghost) {
   CU(cudaMalloc(&s->ghost_off, sizeof(int64_t) * (size_t)nghost));
   CU(cudaMemcpy(s->ghost_off, off.data(), sizeof(int64_t) * (size_t)nghost, cudaMemcpyHostToDevice));
   s->nghost = nghost;
+  return AB200_OK;
+}
+
+struct HaloBlob {
+  cudaIpcMemHandle_t ghost, hflags;
+  int64_t nghost;
+  int magic;
+};
+static_assert(sizeof(HaloBlob) <= AB200_COMM_BLOB_BYTES, "blob too large");
+
+int ab200_halo_export(ab200_solver* s, void* blob) {
+  REQUIRE(s != nullptr && blob != nullptr, "null argument");
+  if (s->nranks <= 1) return set_err(AB200_ESTATE, "ab200_halo_export needs ab200_comm_connect first");
+  CU(cudaSetDevice(s->device));
+  if (!s->hflags) {
+    CU(cudaMalloc(&s->hflags, sizeof(unsigned long long) * kMaxRanks));
+    CU(cudaMemset(s->hflags, 0, sizeof(unsigned long long) * kMaxRanks));
+    CU(cudaMalloc(&s->push_ticket, sizeof(unsigned)));
+    CU(cudaMemset(s->push_ticket, 0, sizeof(unsigned)));
+  }
+  if (!s->ghost) {  // a rank that reads nothing remote still owns a (1-entry) buffer to export
+    CU(cudaMalloc(&s->ghost, sizeof(cplx)));
+  }
+  CU(cudaDeviceSynchronize());
+  HaloBlob b;
+  memset(&b, 0, sizeof(b));
+  CU(cudaIpcGetMemHandle(&b.ghost, s->ghost));
+  CU(cudaIpcGetMemHandle(&b.hflags, s->hflags));
+  b.nghost = s->nghost;
+  b.magic = 0xab201;
+  memset(blob, 0, AB200_COMM_BLOB_BYTES);
+  memcpy(blob, &b, sizeof(b));
+  return AB200_OK;
+}
+
+int ab200_halo_connect(ab200_solver* s, const void* blobs, const int64_t* send_idx,
+                       const int64_t* send_ptr, const int64_t* dst_off) {
+  REQUIRE(s != nullptr && blobs != nullptr && send_ptr != nullptr && dst_off != nullptr,
+          "null argument");
+  if (!s->hflags) return set_err(AB200_ESTATE, "ab200_halo_connect before ab200_halo_export");
+  CU(cudaSetDevice(s->device));
+  const unsigned char* bl = static_cast<const unsigned char*>(blobs);
+  REQUIRE(send_ptr[0] == 0, "send_ptr[0] must be 0");
+  for (int r = 0; r < s->nranks; ++r) {
+    REQUIRE(send_ptr[r + 1] >= send_ptr[r], "send_ptr must be non-decreasing");
+    s->send_ptr[r] = send_ptr[r];
+    s->dst_off[r] = dst_off[r];
+    if (r == s->rank) {
+      REQUIRE(send_ptr[r + 1] == send_ptr[r], "a rank does not send to itself");
+      continue;
+    }
+    HaloBlob b;
+    memcpy(&b, bl + (size_t)r * AB200_COMM_BLOB_BYTES, sizeof(b));
+    REQUIRE(b.magic == 0xab201, "halo blob of rank %d is invalid", r);
+    REQUIRE(dst_off[r] >= 0 && dst_off[r] + (send_ptr[r + 1] - send_ptr[r]) <= (b.nghost > 0 ? b.nghost : 1),
+            "entries for rank %d overflow its ghost buffer", r);
+    CU(cudaIpcOpenMemHandle(&s->peer_ghost[r], b.ghost, cudaIpcMemLazyEnablePeerAccess));
+    CU(cudaIpcOpenMemHandle(&s->peer_hflags[r], b.hflags, cudaIpcMemLazyEnablePeerAccess));
+  }
+  for (int r = s->nranks; r <= kMaxRanks; ++r) s->send_ptr[r] = send_ptr[s->nranks];
+  const int64_t nsend = send_ptr[s->nranks];
+  for (int64_t k = 0; k < nsend; ++k)
+    REQUIRE(send_idx[k] >= 0 && send_idx[k] < s->n, "send_idx[%lld] out of the local block", (long long)k);
+  cudaFree(s->send_idx);
+  s->send_idx = nullptr;
+  CU(cudaMalloc(&s->send_idx, sizeof(int64_t) * (size_t)(nsend > 0 ? nsend : 1)));
+  if (nsend > 0)
+    CU(cudaMemcpy(s->send_idx, send_idx, sizeof(int64_t) * (size_t)nsend, cudaMemcpyHostToDevice));
+  s->push = true;
+  s->hseq = 0;
   return AB200_OK;
 }
 

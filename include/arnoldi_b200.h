@@ -153,6 +153,15 @@ int ab200_comm_export(ab200_solver *s, void *blob);
 int ab200_comm_connect(ab200_solver *s, int rank, int nranks, const void *blobs,
                        const int64_t *row_starts);
 int ab200_set_halo(ab200_solver *s, const int64_t *ghost_cols, int64_t nghost);
+/* Optional owner-side push of the halo (for scattered halos).  After ab200_set_halo on every
+ * rank: ab200_halo_export writes a blob with the IPC handles of this rank's ghost buffer and
+ * delivery flags; ab200_halo_connect takes all ranks' blobs plus, for every peer r, the LOCAL
+ * rows of this rank that r reads (send_idx[send_ptr[r] .. send_ptr[r+1]), ascending = the order
+ * of r's ghost_cols) and dst_off[r] = index in r's ghost buffer where this rank's entries start.
+ * From then on ab200_expand pushes instead of pulling. */
+int ab200_halo_export(ab200_solver *s, void *blob);
+int ab200_halo_connect(ab200_solver *s, const void *blobs, const int64_t *send_idx,
+                       const int64_t *send_ptr, const int64_t *dst_off);
 
 /* ---- measurement ---- */
 int ab200_set_timing(ab200_solver *s, int enabled); /* CUDA-event timing per kernel class */

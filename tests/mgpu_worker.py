@@ -33,13 +33,15 @@ def main():
              ("mark50_mgs_s0", mark(50), dict(nev=5, max_dim=20), "mgs")]
     from conftest import lap2d as lap2d_kron
     cases.append(("lap2d64_s0", lap2d_kron(64), dict(nev=10, max_dim=40), "cgs2"))
-    for tag, A, kw, ortho in cases:
+    # every case through both halo exchanges (pull from peer HBM / owner-side push)
+    cases = [c + (h,) for c in cases for h in ("pull", "push")]
+    for tag, A, kw, ortho, halo in cases:
         n = A.shape[0]
         np.random.seed(0)
         stats = {}
         Q, T, hist = partial_schur(A, kw["nev"], max_dim=kw["max_dim"], stopping_criterion=1e-8,
                                    max_restarts=1000, sort_function=arg_largest_real,
-                                   ortho=ortho, device=local, comm=comm, stats=stats)
+                                   ortho=ortho, device=local, comm=comm, stats=stats, halo=halo)
         part = RowPartition(n, comm.world)
         r0, r1 = part.rows(rank)
         assert Q.shape == (r1 - r0, kw["nev"])
@@ -57,8 +59,26 @@ def main():
             assert np.sum(rel > 1e-10) <= max(1, len(lam) // 10) and rel.max() < 1e-8, (tag, rel)
             assert res.max() < 1e-7, (tag, res)
             assert np.abs(Qf.conj().T @ Qf - np.eye(kw["nev"])).max() < 1e-12
-            print(f"[mgpu] {tag}: world={comm.world} R={R} (ref {Rref}) max rel {rel.max():.2e} "
+            print(f"[mgpu] {tag} halo={halo}: world={comm.world} R={R} (ref {Rref}) max rel {rel.max():.2e} "
                   f"res {res.max():.2e} second_rounds={stats['second_rounds']}", flush=True)
+    # scattered halo (power-law operator) against the single-process oracle, same seed
+    from arnoldi_b200.matrices import powerlaw
+    import oracle
+    A = powerlaw(40000)
+    for halo in ("pull", "push"):
+        np.random.seed(0)
+        Q, T, hist = partial_schur(A, 10, max_dim=40, stopping_criterion=1e-8, max_restarts=200,
+                                   sort_function=arg_largest_real, device=local, comm=comm,
+                                   halo=halo)
+        if rank == 0:
+            np.random.seed(0)
+            Qo, To, ho = oracle.partial_schur(A, 10, max_dim=40, stopping_criterion=1e-8,
+                                              max_restarts=200,
+                                              sort_function=oracle.arg_largest_real)
+            rel = np.abs(np.diag(T) - np.diag(To)) / np.abs(np.diag(To))
+            assert rel.max() < 1e-10 and int(hist.restarts[0]) == int(ho.restarts[0]), (rel, hist)
+            print(f"[mgpu] powerlaw halo={halo}: R={int(hist.restarts[0])} max rel {rel.max():.2e}",
+                  flush=True)
     comm.barrier()
     dist.destroy_process_group()
     if rank == 0:
