@@ -11,17 +11,18 @@
 //     coalesced 128-bit loads, then one thread per row walks its segment in STORED
 //     ORDER with separate multiply and add -- the same operation order as scipy's
 //     csr_matvec, so for rows handled this way y is bit-identical to scipy;
-//   * a row whose part of the tile is long (>= kLongRow entries) is summed by the
-//     whole block instead (fixed-order tree), and a row longer than a tile is carried
-//     across the block's tile iterations through y.
+//   * a row whose part of the tile is longer than kShortRow (16) entries is summed by a whole
+//     warp instead (lanes stride the segment, fixed-order butterfly: deterministic, but not
+//     scipy's order), and a row longer than a tile is carried across the block's tile
+//     iterations through y.  Without this, one thread walking a 100-entry row serialises
+//     the block on power-law matrices.
 // x is gathered with 128-bit read-only loads; for banded matrices consecutive rows
 // gather consecutive x entries, so the gathers coalesce and hit L2.
 #include "kernels.cuh"
 
 namespace ab200 {
 
-constexpr int kLongRow = 96;
-constexpr int kMaxLongPerTile = 64;
+constexpr int kShortRow = 16;  // segments up to this long are summed by one thread, in stored order
 
 template <typename T>
 struct ValOps;
@@ -74,8 +75,8 @@ __global__ void __launch_bounds__(kSpmvThreads) spmv_tile_kernel(SpmvArgs a) {
   ValT* sval = reinterpret_cast<ValT*>(smem_raw);
   int32_t* scol = reinterpret_cast<int32_t*>(smem_raw + (size_t)(a.tile + 4) * sizeof(ValT));
   __shared__ int s_nlong;
-  __shared__ int64_t s_long_row[kMaxLongPerTile];
-  __shared__ cplx s_red[kSpmvThreads / kWarp];
+  int64_t* s_long_row = reinterpret_cast<int64_t*>(
+      smem_raw + (size_t)(a.tile + 4) * (sizeof(ValT) + sizeof(int32_t)) + 8);  // [tile / 16 + 1]
 
   const IdxT* __restrict__ indptr = static_cast<const IdxT*>(a.indptr);
   const ValT* __restrict__ values = static_cast<const ValT*>(a.values);
@@ -126,12 +127,10 @@ __global__ void __launch_bounds__(kSpmvThreads) spmv_tile_kernel(SpmvArgs a) {
         const int64_t lo = rs > cs ? rs : cs;
         const int64_t hi = re < ce ? re : ce;
         const int len = (int)(hi - lo);
-        if (len >= kLongRow) {
+        if (len > kShortRow) {  // handed to a whole warp below
           const int slot = atomicAdd(&s_nlong, 1);
-          if (slot < kMaxLongPerTile) {
-            s_long_row[slot] = row;
-            continue;
-          }
+          s_long_row[slot] = row;
+          continue;
         }
         cplx acc = (rs < cs) ? a.y[row] : make_double2(0.0, 0.0);
         int k = (int)(lo - ca);
@@ -155,29 +154,25 @@ __global__ void __launch_bounds__(kSpmvThreads) spmv_tile_kernel(SpmvArgs a) {
         a.y[row] = acc;
       }
       __syncthreads();
-      // ---- long rows: the whole block reduces one row segment at a time
-      const int nlong = s_nlong < kMaxLongPerTile ? s_nlong : kMaxLongPerTile;
-      for (int l = 0; l < nlong; ++l) {
+      // ---- longer segments: one warp per row, lanes stride the segment, fixed-order butterfly
+      const int nlong = s_nlong;
+      for (int l = (tid >> 5); l < nlong; l += kSpmvThreads / kWarp) {
         const int64_t row = s_long_row[l];
         const int64_t rs = (int64_t)indptr[row], re = (int64_t)indptr[row + 1];
         const int64_t lo = rs > cs ? rs : cs;
         const int64_t hi = re < ce ? re : ce;
         cplx acc = make_double2(0.0, 0.0);
-        for (int k = (int)(lo - ca) + tid; k < (int)(hi - ca); k += kSpmvThreads) {
+        for (int k = (int)(lo - ca) + (tid & 31); k < (int)(hi - ca); k += kWarp) {
           const int64_t col = scol[k];
           const cplx xv = (col < nloc) ? ld_ro(x + col) : ld_ro(ghost + (col - nloc));
           acc = cadd_rn(acc, ValOps<ValT>::mul(sval[k], xv));
         }
         acc = warp_sum(acc);
-        if ((tid & 31) == 0) s_red[tid >> 5] = acc;
-        __syncthreads();
-        if (tid == 0) {
-          cplx t = (rs < cs) ? a.y[row] : make_double2(0.0, 0.0);
-          for (int k = 0; k < kSpmvThreads / kWarp; ++k) t = cadd_rn(t, s_red[k]);
+        if ((tid & 31) == 0) {
+          cplx t = (rs < cs) ? cadd_rn(a.y[row], acc) : acc;
           if (re <= ce) t = cscale(t, xs);
           a.y[row] = t;
         }
-        __syncthreads();
       }
     }
   }
@@ -198,7 +193,8 @@ cudaError_t launch_spmv_plan(const void* indptr, int indptr_bits, int64_t n, int
 
 template <typename IdxT, typename ValT, int THREADS>
 static cudaError_t launch_spmv_tt(const SpmvArgs& a, cudaStream_t st) {
-  const size_t smem = (size_t)(a.tile + 4) * (sizeof(ValT) + sizeof(int32_t));
+  const size_t smem = (size_t)(a.tile + 4) * (sizeof(ValT) + sizeof(int32_t)) + 16 +
+                      sizeof(int64_t) * (size_t)(a.tile / 16 + 2);
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(spmv_tile_kernel<IdxT, ValT, THREADS>,

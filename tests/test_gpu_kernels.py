@@ -60,22 +60,30 @@ def _spmv_cases():
 
 @pytest.mark.parametrize("name", list(_spmv_cases()))
 def test_spmv_bit_exact_vs_scipy(gpu, name):
-    """Rows shorter than the long-row threshold are summed in stored order with separate
-    multiply and add, exactly like scipy's csr_matvec: y must match bit for bit."""
+    """Rows of at most 16 entries (all of mark, the Laplacians, most of the random cases) are
+    summed in stored order with separate multiply and add, exactly like scipy's csr_matvec:
+    y must match bit for bit.  Longer rows are summed by a warp (fixed butterfly order):
+    within 1e-13 of the row's absolute sum."""
     A = _spmv_cases()[name]
     n = A.shape[0]
     rng = np.random.default_rng(5)
+    short = np.diff(A.indptr) <= 16
     with _solver(n, 2, A) as dev:
         for x in (_cvec(rng, n), rng.standard_normal(n).astype(np.complex128)):
             y = dev.spmv(x)
-            np.testing.assert_array_equal(y, A @ x)
+            ref = A @ x
+            np.testing.assert_array_equal(y[short], ref[short])
+            scale = abs(A) @ np.abs(x)
+            assert np.all(np.abs(y - ref) <= 1e-13 * scale + 1e-300)
+    if name in ("mark50", "lap2d_40", "lap2d_kron_zeros", "empty_rows"):
+        assert short.all()
 
 
 @pytest.mark.parametrize("tile", [512, 1024, 2048])
 def test_spmv_skewed_rows_and_int64_indptr(gpu, tile):
     """Power-law row lengths: rows longer than a tile are carried across tile iterations,
-    long segments are tree-reduced by the block (not stored order => tolerance 1e-13
-    relative to the row's absolute sum instead of bit-exact)."""
+    segments longer than 16 entries are reduced by a warp (not stored order => tolerance
+    1e-13 relative to the row's absolute sum instead of bit-exact)."""
     rng = np.random.default_rng(3)
     n = 6000
     lens = np.minimum((rng.pareto(1.2, n) * 3).astype(np.int64) + 1, n)
@@ -97,7 +105,7 @@ def test_spmv_skewed_rows_and_int64_indptr(gpu, tile):
             dev.set_csr(ip, indices, data)
             y = dev.spmv(x)
         assert np.all(np.abs(y - ref) <= 1e-13 * scale + 1e-300)
-        short = lens < 96
+        short = lens <= 16
         np.testing.assert_array_equal(y[short], ref[short])
 
 
