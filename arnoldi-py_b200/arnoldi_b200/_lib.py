@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libarnoldi_b200.so")
+LIB_PATH = os.environ.get("AB200_LIB_PATH") or os.path.join(_HERE, "libarnoldi_b200.so")
 
 ABI_VERSION = 1
 OK, EINVAL, ECUDA, ENOMEM, ESTATE, ECOMM = 0, -1, -2, -3, -4, -5

@@ -55,11 +55,14 @@ struct SpmvArgs {
   int nblocks;
   int tile;                // nnz staged per block iteration
   int threads;             // block size: 128 or 256
+  int long_rows;           // some row has more than 16 entries: warp-per-row path compiled in
   const StepCtl* ctl;      // nullptr for the stand-alone entry point
 };
 
 cudaError_t launch_spmv(const SpmvArgs& a, int indptr_bits, int value_kind, cudaStream_t st);
 // builds rowblk[b] = first row whose indptr >= b * tile  (b = 0..nblocks), on device
+cudaError_t launch_spmv_maxrow(const void* indptr, int indptr_bits, int64_t n, int* out,
+                               cudaStream_t st);
 cudaError_t launch_spmv_plan(const void* indptr, int indptr_bits, int64_t n, int64_t nnz, int tile,
                              int nblocks, int64_t* rowblk, cudaStream_t st);
 

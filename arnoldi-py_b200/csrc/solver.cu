@@ -92,6 +92,7 @@ struct ab200_solver {
   int nblk = 0;
   int tile = 0;
   int spmv_threads = 128;
+  int max_row_len = 0;
   cplx* ghost = nullptr;
   int64_t n_local_cols = 0;
 
@@ -477,7 +478,14 @@ int ab200_set_csr(ab200_solver* s, const void* indptr, int indptr_bits, const in
   REQUIRE(nblk < (1ll << 30), "too many SpMV tiles");
   CU(cudaMalloc(&s->rowblk, sizeof(int64_t) * 2 * (size_t)(nblk + 1)));
   CU(launch_spmv_plan(s->indptr, indptr_bits, s->n, nnz, tile, (int)nblk, s->rowblk, s->stream));
+  // longest row decides whether the SpMV needs its warp-per-row path at all
+  CU(cudaMemsetAsync(s->ticket, 0, sizeof(unsigned), s->stream));
+  CU(launch_spmv_maxrow(s->indptr, indptr_bits, s->n, reinterpret_cast<int*>(s->ticket), s->stream));
+  int maxrow = 0;
+  CU(cudaMemcpyAsync(&maxrow, s->ticket, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
   CU(cudaStreamSynchronize(s->stream));
+  CU(cudaMemsetAsync(s->ticket, 0, sizeof(unsigned), s->stream));
+  s->max_row_len = maxrow;
   s->indptr_bits = indptr_bits;
   s->value_kind = value_kind;
   s->nnz = nnz;
@@ -535,6 +543,7 @@ static int enqueue_spmv(ab200_solver* s, const cplx* x, cplx* y, const double* x
   a.nblocks = s->nblk;
   a.tile = s->tile;
   a.threads = s->spmv_threads;
+  a.long_rows = s->max_row_len > 16 ? 1 : 0;
   a.ctl = in_expand ? s->ctl : nullptr;
   const double sv = s->value_kind == AB200_F64 ? 8.0 : 16.0;
   const double bytes = (double)s->nnz * (sv + 4.0) + (double)s->n * (s->indptr_bits / 8 + 32.0) +

@@ -46,6 +46,22 @@ __device__ __forceinline__ cplx cadd_rn(cplx a, cplx b) {
 }
 
 template <typename IdxT>
+__global__ void spmv_maxrow_kernel(const IdxT* __restrict__ indptr, int64_t n, int* __restrict__ out) {
+  int m = 0;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n;
+       r += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t len = (int64_t)indptr[r + 1] - (int64_t)indptr[r];
+    const int l = len > 0x7fffffff ? 0x7fffffff : (int)len;
+    m = l > m ? l : m;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const int t = __shfl_xor_sync(0xffffffffu, m, o);
+    m = t > m ? t : m;
+  }
+  if ((threadIdx.x & 31) == 0) atomicMax(out, m);  // integer max: order-independent
+}
+
+template <typename IdxT>
 __global__ void spmv_plan_kernel(const IdxT* __restrict__ indptr, int64_t n, int64_t nnz, int tile,
                                  int nblocks, int64_t* __restrict__ rowblk) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -67,7 +83,9 @@ __global__ void spmv_plan_kernel(const IdxT* __restrict__ indptr, int64_t n, int
   rowblk[b] = lo;
 }
 
-template <typename IdxT, typename ValT, int kSpmvThreads>
+// LONG = false: the matrix has no row longer than kShortRow, the warp-per-row machinery is
+// compiled out (lean kernel for banded operators: mark, Laplacians).
+template <typename IdxT, typename ValT, int kSpmvThreads, bool LONG>
 __global__ void __launch_bounds__(kSpmvThreads) spmv_tile_kernel(SpmvArgs a) {
   if (a.ctl != nullptr && a.ctl->stop) return;
 
@@ -127,7 +145,7 @@ __global__ void __launch_bounds__(kSpmvThreads) spmv_tile_kernel(SpmvArgs a) {
         const int64_t lo = rs > cs ? rs : cs;
         const int64_t hi = re < ce ? re : ce;
         const int len = (int)(hi - lo);
-        if (len > kShortRow) {  // handed to a whole warp below
+        if (LONG && len > kShortRow) {  // handed to a whole warp below
           const int slot = atomicAdd(&s_nlong, 1);
           s_long_row[slot] = row;
           continue;
@@ -135,6 +153,7 @@ __global__ void __launch_bounds__(kSpmvThreads) spmv_tile_kernel(SpmvArgs a) {
         cplx acc = (rs < cs) ? a.y[row] : make_double2(0.0, 0.0);
         int k = (int)(lo - ca);
         const int kend = (int)(hi - ca);
+
         for (; k + 4 <= kend; k += 4) {
           cplx xv[4];
 #pragma unroll
@@ -145,6 +164,7 @@ __global__ void __launch_bounds__(kSpmvThreads) spmv_tile_kernel(SpmvArgs a) {
 #pragma unroll
           for (int u = 0; u < 4; ++u) acc = cadd_rn(acc, ValOps<ValT>::mul(sval[k + u], xv[u]));
         }
+
         for (; k < kend; ++k) {
           const int64_t col = scol[k];
           const cplx xv = (col < nloc) ? ld_ro(x + col) : ld_ro(ghost + (col - nloc));
@@ -155,7 +175,7 @@ __global__ void __launch_bounds__(kSpmvThreads) spmv_tile_kernel(SpmvArgs a) {
       }
       __syncthreads();
       // ---- longer segments: one warp per row, lanes stride the segment, fixed-order butterfly
-      const int nlong = s_nlong;
+      const int nlong = LONG ? s_nlong : 0;
       for (int l = (tid >> 5); l < nlong; l += kSpmvThreads / kWarp) {
         const int64_t row = s_long_row[l];
         const int64_t rs = (int64_t)indptr[row], re = (int64_t)indptr[row + 1];
@@ -178,6 +198,18 @@ __global__ void __launch_bounds__(kSpmvThreads) spmv_tile_kernel(SpmvArgs a) {
   }
 }
 
+cudaError_t launch_spmv_maxrow(const void* indptr, int indptr_bits, int64_t n, int* out,
+                               cudaStream_t st) {
+  int64_t grid = (n + 255) / 256;
+  if (grid > 148 * 8) grid = 148 * 8;
+  if (grid < 1) grid = 1;
+  if (indptr_bits == 32)
+    spmv_maxrow_kernel<int32_t><<<(int)grid, 256, 0, st>>>(static_cast<const int32_t*>(indptr), n, out);
+  else
+    spmv_maxrow_kernel<int64_t><<<(int)grid, 256, 0, st>>>(static_cast<const int64_t*>(indptr), n, out);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_spmv_plan(const void* indptr, int indptr_bits, int64_t n, int64_t nnz, int tile,
                              int nblocks, int64_t* rowblk, cudaStream_t st) {
   const int threads = 256;
@@ -191,19 +223,24 @@ cudaError_t launch_spmv_plan(const void* indptr, int indptr_bits, int64_t n, int
   return cudaGetLastError();
 }
 
-template <typename IdxT, typename ValT, int THREADS>
-static cudaError_t launch_spmv_tt(const SpmvArgs& a, cudaStream_t st) {
+template <typename IdxT, typename ValT, int THREADS, bool LONG>
+static cudaError_t launch_spmv_ttl(const SpmvArgs& a, cudaStream_t st) {
   const size_t smem = (size_t)(a.tile + 4) * (sizeof(ValT) + sizeof(int32_t)) + 16 +
                       sizeof(int64_t) * (size_t)(a.tile / 16 + 2);
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(spmv_tile_kernel<IdxT, ValT, THREADS>,
+    cudaFuncSetAttribute(spmv_tile_kernel<IdxT, ValT, THREADS, LONG>,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     attr_done = true;
   }
   const int grid = a.nblocks;  // one tile per block; blocks are small and many per SM
-  spmv_tile_kernel<IdxT, ValT, THREADS><<<grid, THREADS, smem, st>>>(a);
+  spmv_tile_kernel<IdxT, ValT, THREADS, LONG><<<grid, THREADS, smem, st>>>(a);
   return cudaGetLastError();
+}
+template <typename IdxT, typename ValT, int THREADS>
+static cudaError_t launch_spmv_tt(const SpmvArgs& a, cudaStream_t st) {
+  return a.long_rows ? launch_spmv_ttl<IdxT, ValT, THREADS, true>(a, st)
+                     : launch_spmv_ttl<IdxT, ValT, THREADS, false>(a, st);
 }
 template <typename IdxT, typename ValT>
 static cudaError_t launch_spmv_t(const SpmvArgs& a, cudaStream_t st) {
