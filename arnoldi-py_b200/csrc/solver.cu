@@ -462,6 +462,14 @@ int ab200_set_csr(ab200_solver* s, const void* indptr, int indptr_bits, const in
                        s->stream));
     CU(cudaMemcpyAsync(s->values, values, vb * (size_t)nnz, cudaMemcpyHostToDevice, s->stream));
   }
+  // longest row decides whether the SpMV needs its warp-per-row path at all
+  CU(cudaMemsetAsync(s->ticket, 0, sizeof(unsigned), s->stream));
+  CU(launch_spmv_maxrow(s->indptr, indptr_bits, s->n, reinterpret_cast<int*>(s->ticket), s->stream));
+  int maxrow = 0;
+  CU(cudaMemcpyAsync(&maxrow, s->ticket, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  CU(cudaMemsetAsync(s->ticket, 0, sizeof(unsigned), s->stream));
+  s->max_row_len = maxrow;
   // nnz tile: about one row per thread of the block, within [512, 2048]
   const int threads = s->opt_spmv_threads == 256 ? 256 : 128;  // 128 measured 3% faster
   int tile = s->opt_spmv_tile;
@@ -471,6 +479,7 @@ int ab200_set_csr(ab200_solver* s, const void* indptr, int indptr_bits, const in
     tile = (tile + 127) / 128 * 128;
     if (tile < 512) tile = 512;
     if (tile > 2048) tile = 2048;
+    if (maxrow > 16 && tile > 1280) tile = 1280;  // skewed rows: measured best on the power-law operator
   }
   s->spmv_threads = threads;
   int64_t nblk = (nnz + tile - 1) / tile;
@@ -478,14 +487,7 @@ int ab200_set_csr(ab200_solver* s, const void* indptr, int indptr_bits, const in
   REQUIRE(nblk < (1ll << 30), "too many SpMV tiles");
   CU(cudaMalloc(&s->rowblk, sizeof(int64_t) * 2 * (size_t)(nblk + 1)));
   CU(launch_spmv_plan(s->indptr, indptr_bits, s->n, nnz, tile, (int)nblk, s->rowblk, s->stream));
-  // longest row decides whether the SpMV needs its warp-per-row path at all
-  CU(cudaMemsetAsync(s->ticket, 0, sizeof(unsigned), s->stream));
-  CU(launch_spmv_maxrow(s->indptr, indptr_bits, s->n, reinterpret_cast<int*>(s->ticket), s->stream));
-  int maxrow = 0;
-  CU(cudaMemcpyAsync(&maxrow, s->ticket, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
   CU(cudaStreamSynchronize(s->stream));
-  CU(cudaMemsetAsync(s->ticket, 0, sizeof(unsigned), s->stream));
-  s->max_row_len = maxrow;
   s->indptr_bits = indptr_bits;
   s->value_kind = value_kind;
   s->nnz = nnz;
