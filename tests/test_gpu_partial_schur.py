@@ -203,3 +203,52 @@ def test_partial_schur_powerlaw_vs_oracle(gpu):
     assert (np.linalg.norm(A @ X - X * w, axis=0) / np.abs(w)).max() <= 1e-8
     np.testing.assert_allclose(np.sort(np.diag(T).real)[::-1],
                                6.75 - 0.25 * np.arange(10), atol=1e-3)
+
+
+def test_krylov_schur_relations_at_one_million_rows(gpu):
+    """Size-independent properties at n = 1 048 576 (every kernel runs many waves): after an
+    expansion, a truncation and a second expansion the basis is orthonormal and both
+    Krylov relations hold:  A V_m = V_{m+1} H  with H = [T spike-row; Hessenberg tail]."""
+    from scipy.linalg import schur
+    from arnoldi_b200.matrices import lap2d as lap2d_direct
+    from arnoldi_b200.solver import DeviceSolver
+    from arnoldi_b200.utils import arg_largest_real, ordered_schur, rand_normalized_vector
+    A = lap2d_direct(1024)
+    n, m, p = A.shape[0], 24, 10
+    np.random.seed(1)
+    H = np.zeros((m + 1, m), np.complex128)
+    with DeviceSolver(n, m) as dev:
+        dev.set_csr(A.indptr, A.indices, A.data)
+        dev.set_columns(0, rand_normalized_vector(n, np.complex128))
+
+        def grow(start):
+            cols, k, brk = dev.expand(start, m, 1e-8)
+            assert k == m and not brk
+            for j in range(start, k):
+                H[: j + 2, j] = cols[: j + 2, j]
+
+        def check():
+            V = dev.get_columns(0, m + 1)
+            G = V.conj().T @ V
+            assert np.abs(G - np.eye(m + 1)).max() < 1e-12
+            R = A @ V[:, :m] - V @ H
+            assert np.abs(R).max() < 1e-12 * 8.0
+
+        grow(0)
+        assert np.all(np.abs(np.tril(H[:m, :m], -2)) == 0)      # Hessenberg
+        assert np.all(np.diag(H, -1).real > 0) and np.all(np.diag(H, -1).imag == 0)
+        check()
+        T1, Q1 = schur(H[:m, :m], output="complex")
+        T2, Q2 = ordered_schur(T1, output="complex", sort_function=arg_largest_real)
+        Q = Q1 @ Q2
+        spike = H[m, :m] @ Q[:, :p]
+        dev.restart(Q, m, p)
+        H[:p, :p] = T2[:p, :p]
+        H[p, :p] = spike
+        H[p, p:] = 0
+        H[p + 1:, :p] = 0
+        H[:, p:] = 0
+        grow(p)
+        check()
+        st = dev.stats()
+        assert st["arnoldi_steps"] == m + (m - p)
