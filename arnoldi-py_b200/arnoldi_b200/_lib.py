@@ -31,7 +31,7 @@ class Stats(C.Structure):
                                     "ortho_pass2_launches", "ortho_fused_launches",
                                     "mgs_launches", "restart_launches",
                                     "arnoldi_steps", "ortho_rounds", "second_rounds",
-                                    "kernel_launches")]
+                                    "kernel_launches", "real_storage")]
     )
 
     def as_dict(self):

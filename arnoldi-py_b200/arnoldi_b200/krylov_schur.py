@@ -43,7 +43,7 @@ def partial_schur(
     A, nev, *, max_dim=None, stopping_criterion=None, max_restarts=100,
     sort_function=None, p=None,
     ortho="cgs2", v0=None, device=0, stats=None, raise_on_no_convergence=True, comm=None,
-    halo="auto",
+    halo="auto", real_storage=True,
 ):
     """Partial Schur decomposition ``A Q = Q T`` of the ``nev`` wanted eigenvalues.
 
@@ -60,6 +60,11 @@ def partial_schur(
         scipy CSR matrix (each rank slices its block of rows) or this rank's ``RowBlock``; every
         rank must seed NumPy's global RNG identically (v0 is drawn globally and sliced); the
         returned Q holds this rank's rows only, T and history are identical on all ranks.
+    real_storage : keep the basis as float64 on the device for as long as it is provably real
+        (float64 A, real v0, real Schur vectors so far -- e.g. every symmetric real operator,
+        and the first expansion of any real one); it is converted to complex128 in place the
+        moment a complex Q arrives.  Real parts are what the complex path would compute; the
+        returned arrays are complex128 either way.  False forces complex128 storage throughout.
     halo  : "pull" (each rank gathers the remote entries of v it needs straight from peer HBM),
         "push" (the owner gathers locally and streams them into the peer's buffer) or "auto"
         (push when some rank's halo has more than 65 536 scattered entries)
@@ -113,6 +118,8 @@ def partial_schur(
 
     lap("host_prepare")
     with DeviceSolver(n, max_dim, **solver_args) as dev:
+        if not real_storage:
+            dev.set_option("real_mode", 0)
         lap("device_alloc")
         if stats is not None:
             dev.set_timing(True)

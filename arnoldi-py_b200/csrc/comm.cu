@@ -21,9 +21,18 @@ __global__ void __launch_bounds__(256) halo_gather_kernel(HaloArgs a) {
 #pragma unroll
     for (int r = 1; r < kMaxRanks; ++r)
       if (r < a.nranks && k >= a.seg_start[r]) q = r;
-    const cplx* src = a.peer_base[q] + (int64_t)a.col * a.peer_ld[q] + a.src_off[k];
     // peer memory: plain coherent load (it was written by another GPU)
-    a.ghost[k] = ld_plain(src);
+    if (a.real) {
+      // real storage: a column is peer_ld[q] complex slots = 2 * peer_ld[q] doubles
+      const double* src = reinterpret_cast<const double*>(a.peer_base[q]) +
+                          (int64_t)a.col * a.peer_ld[q] + a.src_off[k];
+      double v;
+      asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(src) : "memory");
+      reinterpret_cast<double*>(a.ghost)[k] = v;
+    } else {
+      const cplx* src = a.peer_base[q] + (int64_t)a.col * a.peer_ld[q] + a.src_off[k];
+      a.ghost[k] = ld_plain(src);
+    }
   }
 }
 
@@ -42,9 +51,15 @@ __global__ void __launch_bounds__(256) halo_push_kernel(HaloPushArgs a) {
 #pragma unroll
     for (int q = 1; q < kMaxRanks; ++q)
       if (q < a.nranks && k >= a.send_ptr[q]) r = q;
-    cplx v = ld_ro(src + a.send_idx[k]);
-    cplx* dst = a.peer_ghost[r] + a.dst_off[r] + (k - a.send_ptr[r]);
-    asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(dst), "d"(v.x), "d"(v.y) : "memory");
+    if (a.real) {
+      const double v = __ldg(reinterpret_cast<const double*>(src) + a.send_idx[k]);
+      double* dst = reinterpret_cast<double*>(a.peer_ghost[r]) + a.dst_off[r] + (k - a.send_ptr[r]);
+      asm volatile("st.global.f64 [%0], %1;" ::"l"(dst), "d"(v) : "memory");
+    } else {
+      cplx v = ld_ro(src + a.send_idx[k]);
+      cplx* dst = a.peer_ghost[r] + a.dst_off[r] + (k - a.send_ptr[r]);
+      asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(dst), "d"(v.x), "d"(v.y) : "memory");
+    }
   }
   __shared__ int s_last;
   __threadfence_system();

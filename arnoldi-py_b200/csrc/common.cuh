@@ -70,6 +70,35 @@ __device__ __forceinline__ void cfms(cplx& acc, const cplx a, const cplx b) {
   acc.y = fma(-a.x, b.y, acc.y);
   acc.y = fma(-a.y, b.x, acc.y);
 }
+// ---- the same three updates when the basis is stored REAL: one 16-byte element then holds
+// two consecutive real rows (x = row 2k, y = row 2k+1) and every coefficient is real (.x)
+template <bool REAL>
+__device__ __forceinline__ void dotacc(cplx& acc, const cplx a, const cplx b) {
+  if (REAL) {
+    acc.x = fma(a.x, b.x, acc.x);
+    acc.x = fma(a.y, b.y, acc.x);
+  } else {
+    cfma_conj(acc, a, b);
+  }
+}
+template <bool REAL>
+__device__ __forceinline__ void addax(cplx& acc, const cplx a, const cplx c) {
+  if (REAL) {
+    acc.x = fma(a.x, c.x, acc.x);
+    acc.y = fma(a.y, c.x, acc.y);
+  } else {
+    cfma(acc, a, c);
+  }
+}
+template <bool REAL>
+__device__ __forceinline__ void subax(cplx& acc, const cplx a, const cplx c) {
+  if (REAL) {
+    acc.x = fma(-a.x, c.x, acc.x);
+    acc.y = fma(-a.y, c.x, acc.y);
+  } else {
+    cfms(acc, a, c);
+  }
+}
 __device__ __forceinline__ cplx cadd(const cplx a, const cplx b) {
   return make_double2(a.x + b.x, a.y + b.y);
 }

@@ -10,8 +10,9 @@ namespace ab200 {
 struct OrthoArgs {
   const cplx* U;     // basis, column-major, un-normalised columns (V_i = scale[i] * U_i)
   cplx* w;           // vector being orthogonalised (column j+1 of the basis, or a scratch vector)
-  int64_t n;         // local rows
-  int64_t ld;        // leading dimension of U in elements
+  int64_t n;         // 16-byte elements per column: local rows, or ceil(rows / 2) pairs when real
+  int64_t ld;        // leading dimension of U in 16-byte elements
+  int real;          // basis stored real: an element is two consecutive real rows
   int ncols;         // c = number of basis columns to orthogonalise against
   int j;             // Arnoldi step (H column) -- ncols - 1 inside an expansion
   int round;         // 1 or 2 (DGKS repeat)
@@ -46,9 +47,10 @@ struct SpmvArgs {
   const int32_t* indices;  // [nnz] column ids: < n_local -> local x, else ghost[id - n_local]
   const void* values;      // [nnz] float64 or complex128
   const int64_t* rowblk;   // [nblocks + 1] first row of each nnz tile
-  const cplx* x;           // local part of the input vector (un-normalised column)
-  const cplx* ghost;       // halo entries received from peers (nullptr on one GPU)
-  cplx* y;                 // output (local rows)
+  const void* x;           // local part of the input vector: complex128, or float64 when real
+  const void* ghost;       // halo entries received from peers (nullptr on one GPU), same type
+  void* y;                 // output (local rows), same type
+  int real;                // vectors are float64 (basis stored real)
   const double* xscale;    // nullptr or pointer to the lazy scale of x
   int64_t n;               // local rows
   int64_t n_local_cols;    // column ids below this are local
@@ -75,6 +77,7 @@ struct HaloArgs {
   cplx* ghost;                       // [nghost] destination
   int64_t nghost;
   int col;                           // basis column to fetch
+  int real;                          // columns hold float64 (column stride = peer_ld doubles... see kernel)
   int nranks;
   const StepCtl* ctl;
 };
@@ -91,6 +94,7 @@ struct HaloPushArgs {
   unsigned long long seq;
   unsigned* ticket;
   int rank, nranks;
+  int real;                               // entries are float64
   const StepCtl* ctl;
 };
 cudaError_t launch_halo_push(const HaloPushArgs& a, int num_sms, cudaStream_t st);
@@ -104,8 +108,13 @@ struct RestartArgs {
   int m, p;
   const cplx* q;        // device copy of Q[:, :p], row i pre-multiplied by scale[i]; layout [i * p + k]
   double scale_m;       // scale of column m (applied while it is copied to column p)
+  int real;             // basis stored real: n, ld count pairs of rows and q is real (.x)
 };
 cudaError_t launch_restart(const RestartArgs& a, int num_sms, cudaStream_t st, int variant);
+
+cudaError_t launch_pack_real(const cplx* src, double* dst, int64_t n, int num_sms, cudaStream_t st);
+cudaError_t launch_unpack_real(const double* src, cplx* dst, int64_t n, double scale, int num_sms,
+                               cudaStream_t st);
 
 // U[:, col] *= scale[col]; scale[col] = 1   for col in [col0, col0 + ncols)
 cudaError_t launch_materialize(cplx* U, int64_t n, int64_t ld, int col0, int ncols, double* scale,

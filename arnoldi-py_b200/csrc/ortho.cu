@@ -139,7 +139,7 @@ __device__ void finish_norm(const OrthoArgs& a, double nrmsq) {
 // re-used through L1); warp k owns columns [k*CT, k*CT+CT) and keeps their
 // accumulators in registers for the whole kernel.  Lanes run along n, so each
 // load instruction of a warp covers 512 contiguous bytes of one column.
-template <int CT, int R>
+template <int CT, int R, bool REAL>
 __global__ void __launch_bounds__(CT < 8 ? 256 : 512) cgs_pass1_kernel(OrthoArgs a) {
   StepCtl* ctl = a.ctl;
   if (ctl->stop) return;
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(CT < 8 ? 256 : 512) cgs_pass1_kernel(OrthoArgs
     for (int k = 0; k < CT; ++k) {
       if (k < mycols) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) cfma_conj(acc[k], v[k][r], wv[r]);
+        for (int r = 0; r < R; ++r) dotacc<REAL>(acc[k], v[k][r], wv[r]);
       }
     }
     if (warp == 0) {
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(CT < 8 ? 256 : 512) cgs_pass1_kernel(OrthoArgs
 // ------------------------------------------------------------------ CGS pass 2
 // w -= U * coef ; ||w||^2.  Warp = R*32 contiguous rows, all c columns; the
 // coefficients sit in shared memory and are broadcast.
-template <int R, int UC>
+template <int R, int UC, bool REAL>
 __global__ void __launch_bounds__(256) cgs_pass2_kernel(OrthoArgs a) {
   StepCtl* ctl = a.ctl;
   if (ctl->stop) return;
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(256) cgs_pass2_kernel(OrthoArgs a) {
         for (int u = 0; u < UC; ++u) {
           const cplx cf = scoef[i + u];
 #pragma unroll
-          for (int r = 0; r < R; ++r) cfms(acc[r], v[u][r], cf);
+          for (int r = 0; r < R; ++r) subax<REAL>(acc[r], v[u][r], cf);
         }
       }
     }
@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(256) cgs_pass2_kernel(OrthoArgs a) {
       }
       const cplx cf = scoef[i];
 #pragma unroll
-      for (int r = 0; r < R; ++r) cfms(acc[r], v[r], cf);
+      for (int r = 0; r < R; ++r) subax<REAL>(acc[r], v[r], cf);
     }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -368,7 +368,7 @@ __device__ __forceinline__ void cp_async_wait() {
 // PF = true: the block's NEXT chunk is staged into shared memory with cp.async (LDGSTS,
 // no registers held) while the current one is processed, so requests stay in flight across
 // the block barrier.  PF = false: plain register loads (more blocks per SM instead).
-template <int CT, int R, bool PF>
+template <int CT, int R, bool PF, bool REAL>
 __global__ void __launch_bounds__(CT < 5 ? 256 : 512) cgs_fused_kernel(OrthoArgs a) {
   StepCtl* ctl = a.ctl;
   if (ctl->stop) return;
@@ -481,7 +481,7 @@ __global__ void __launch_bounds__(CT < 5 ? 256 : 512) cgs_fused_kernel(OrthoArgs
       cplx t = make_double2(0.0, 0.0);
 #pragma unroll
       for (int k = 0; k < CT; ++k)
-        if (k < mycols) cfma(t, v[k][r], cf[k]);
+        if (k < mycols) addax<REAL>(t, v[k][r], cf[k]);
       mine[r * kWarp + lane] = t;
     }
     __syncthreads();  // partial sums (and, PF, warp 0's chunk of w) visible to the block
@@ -521,7 +521,7 @@ __global__ void __launch_bounds__(CT < 5 ? 256 : 512) cgs_fused_kernel(OrthoArgs
     for (int k = 0; k < CT; ++k) {
       if (k < mycols) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) cfma_conj(acc[k], v[k][r], wv[r]);
+        for (int r = 0; r < R; ++r) dotacc<REAL>(acc[k], v[k][r], wv[r]);
       }
     }
   }
@@ -583,7 +583,7 @@ __global__ void __launch_bounds__(CT < 5 ? 256 : 512) cgs_fused_kernel(OrthoArgs
 //   if i < c:  g_i = <U_i, w>                     (dot with the next column)
 //   if i == 0 and round 1: also ||w||^2           (ortho.py:36)
 //   if i == c: ||w||^2 of the result              (ortho.py:43 / :52)
-template <int R>
+template <int R, bool REAL>
 __global__ void __launch_bounds__(256) mgs_step_kernel(OrthoArgs a, int i) {
   StepCtl* ctl = a.ctl;
   if (ctl->stop) return;
@@ -621,10 +621,10 @@ __global__ void __launch_bounds__(256) mgs_step_kernel(OrthoArgs a, int i) {
     for (int r = 0; r < R; ++r) {
       const bool ok = base + r * kWarp < a.n;
       if (do_axpy) {
-        cfms(wv[r], up[r], cf);
+        subax<REAL>(wv[r], up[r], cf);
         if (ok) st_stream(w + base + r * kWarp, wv[r]);
       }
-      if (do_dot) cfma_conj(dacc, uc[r], wv[r]);
+      if (do_dot) dotacc<REAL>(dacc, uc[r], wv[r]);
       if (norm_in || !do_dot) {
         nacc = fma(wv[r].x, wv[r].x, nacc);
         nacc = fma(wv[r].y, wv[r].y, nacc);
@@ -716,19 +716,25 @@ static void pass1_shape(int c, int* ct, int* warps) {
 template <typename K>
 static int resident_blocks(K kernel, int threads, size_t smem, int* cache);
 
-template <int CT, int R>
-static cudaError_t launch_pass1_t(const OrthoArgs& a, int warps, int num_sms, cudaStream_t st,
-                                  int grid_mult) {
+template <int CT, int R, bool REAL>
+static cudaError_t launch_pass1_tr(const OrthoArgs& a, int warps, int num_sms, cudaStream_t st,
+                                   int grid_mult) {
   OrthoArgs args = a;
   const int threads = warps * kWarp;
   const int64_t nchunks = (a.n + kWarp * R - 1) / (kWarp * R);
   const size_t smem = sizeof(double) * (2 * a.ncols + 2);
   static int occ[17] = {0};
   const int bps = grid_mult > 0 ? grid_mult
-                                : resident_blocks(cgs_pass1_kernel<CT, R>, threads, smem, &occ[warps]);
+                                : resident_blocks(cgs_pass1_kernel<CT, R, REAL>, threads, smem, &occ[warps]);
   const int grid = pick_grid(nchunks, bps, num_sms, a.grid_cap);
-  cgs_pass1_kernel<CT, R><<<grid, threads, smem, st>>>(args);
+  cgs_pass1_kernel<CT, R, REAL><<<grid, threads, smem, st>>>(args);
   return cudaGetLastError();
+}
+template <int CT, int R>
+static cudaError_t launch_pass1_t(const OrthoArgs& a, int warps, int num_sms, cudaStream_t st,
+                                  int grid_mult) {
+  return a.real ? launch_pass1_tr<CT, R, true>(a, warps, num_sms, st, grid_mult)
+                : launch_pass1_tr<CT, R, false>(a, warps, num_sms, st, grid_mult);
 }
 
 cudaError_t launch_cgs_pass1(const OrthoArgs& a, int num_sms, cudaStream_t st, int grid_mult) {
@@ -760,9 +766,9 @@ static int resident_blocks(K kernel, int threads, size_t smem, int* cache) {
   return *cache;
 }
 
-template <int CT, int R, bool PF>
-static cudaError_t launch_fused_t(const OrthoArgs& a, int warps, int num_sms, cudaStream_t st,
-                                  int grid_mult) {
+template <int CT, int R, bool PF, bool REAL>
+static cudaError_t launch_fused_tr(const OrthoArgs& a, int warps, int num_sms, cudaStream_t st,
+                                   int grid_mult) {
   OrthoArgs args = a;
   args.accumulate = 1;  // the dots it produces belong to round 2
   const int threads = warps * kWarp;
@@ -775,16 +781,22 @@ static cudaError_t launch_fused_t(const OrthoArgs& a, int warps, int num_sms, cu
   static int occ[17] = {0};
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(cgs_fused_kernel<CT, R, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncSetAttribute(cgs_fused_kernel<CT, R, PF, REAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          200 * 1024);
     attr_done = true;
   }
   const int bps = grid_mult > 0 ? grid_mult
-                                : resident_blocks(cgs_fused_kernel<CT, R, PF>, threads, smem,
+                                : resident_blocks(cgs_fused_kernel<CT, R, PF, REAL>, threads, smem,
                                                   &occ[warps]);
   const int grid = pick_grid(nchunks, bps, num_sms, a.grid_cap);
-  cgs_fused_kernel<CT, R, PF><<<grid, threads, smem, st>>>(args);
+  cgs_fused_kernel<CT, R, PF, REAL><<<grid, threads, smem, st>>>(args);
   return cudaGetLastError();
+}
+template <int CT, int R, bool PF>
+static cudaError_t launch_fused_t(const OrthoArgs& a, int warps, int num_sms, cudaStream_t st,
+                                  int grid_mult) {
+  return a.real ? launch_fused_tr<CT, R, PF, true>(a, warps, num_sms, st, grid_mult)
+                : launch_fused_tr<CT, R, PF, false>(a, warps, num_sms, st, grid_mult);
 }
 
 // variant 0: cp.async-staged (prefetching) kernel; variant 2: register loads only.
@@ -838,7 +850,10 @@ cudaError_t launch_cgs_pass2(const OrthoArgs& a, int num_sms, cudaStream_t st, i
   const int64_t nblocks = (nchunks + (THREADS / kWarp) - 1) / (THREADS / kWarp);
   const int grid = pick_grid(nblocks, grid_mult > 0 ? grid_mult : 4, num_sms, a.grid_cap);
   const size_t smem = sizeof(cplx) * (a.ncols + 1);
-  cgs_pass2_kernel<R, UC><<<grid, THREADS, smem, st>>>(a);
+  if (a.real)
+    cgs_pass2_kernel<R, UC, true><<<grid, THREADS, smem, st>>>(a);
+  else
+    cgs_pass2_kernel<R, UC, false><<<grid, THREADS, smem, st>>>(a);
   return cudaGetLastError();
 }
 
@@ -848,7 +863,10 @@ cudaError_t launch_mgs_step(const OrthoArgs& a, int i, int num_sms, cudaStream_t
   const int64_t nchunks = (a.n + kWarp * R - 1) / (kWarp * R);
   const int64_t nblocks = (nchunks + (THREADS / kWarp) - 1) / (THREADS / kWarp);
   const int grid = pick_grid(nblocks, grid_mult > 0 ? grid_mult : 4, num_sms, a.grid_cap);
-  mgs_step_kernel<R><<<grid, THREADS, 0, st>>>(a, i);
+  if (a.real)
+    mgs_step_kernel<R, true><<<grid, THREADS, 0, st>>>(a, i);
+  else
+    mgs_step_kernel<R, false><<<grid, THREADS, 0, st>>>(a, i);
   return cudaGetLastError();
 }
 

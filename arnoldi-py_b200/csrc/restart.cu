@@ -20,7 +20,7 @@ __device__ __forceinline__ cplx ld_pinned(const cplx* p) {
   return r;
 }
 
-template <int PT, bool QS>
+template <int PT, bool QS, bool REAL>
 __global__ void __launch_bounds__(512) restart_kernel(RestartArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int m = a.m, p = a.p;
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(512) restart_kernel(RestartArgs a) {
           const int qo = (i + t) * p + k0;
 #pragma unroll
           for (int k = 0; k < PT; ++k)
-            if (k < nk) cfma(acc[k], cur[t], QS ? sq_s[qo + k] : __ldg(sq_g + qo + k));
+            if (k < nk) addax<REAL>(acc[k], cur[t], QS ? sq_s[qo + k] : __ldg(sq_g + qo + k));
         }
       }
 #pragma unroll
@@ -92,8 +92,10 @@ static cudaError_t launch_restart_t(const RestartArgs& a, int num_sms, cudaStrea
   if (!qs) smem = 0;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(restart_kernel<PT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         100 * 1024);
+    cudaFuncSetAttribute(restart_kernel<PT, true, true>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(restart_kernel<PT, true, false>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     attr_done = true;
   }
   const int64_t nchunks = (a.n + kWarp - 1) / kWarp;
@@ -103,10 +105,17 @@ static cudaError_t launch_restart_t(const RestartArgs& a, int num_sms, cudaStrea
   int64_t grid = (int64_t)num_sms * bps;
   if (grid > nchunks) grid = nchunks;
   if (grid < 1) grid = 1;
-  if (qs)
-    restart_kernel<PT, true><<<(int)grid, threads, smem, st>>>(a);
-  else
-    restart_kernel<PT, false><<<(int)grid, threads, smem, st>>>(a);
+  if (qs) {
+    if (a.real)
+      restart_kernel<PT, true, true><<<(int)grid, threads, smem, st>>>(a);
+    else
+      restart_kernel<PT, true, false><<<(int)grid, threads, smem, st>>>(a);
+  } else {
+    if (a.real)
+      restart_kernel<PT, false, true><<<(int)grid, threads, smem, st>>>(a);
+    else
+      restart_kernel<PT, false, false><<<(int)grid, threads, smem, st>>>(a);
+  }
   return cudaGetLastError();
 }
 
@@ -133,6 +142,35 @@ __global__ void __launch_bounds__(256) materialize_kernel(cplx* U, int64_t n, in
       col[r] = cscale(col[r], s);
   }
 }
+// real storage <-> complex128: column conversions used at the boundary and at a mode switch
+__global__ void __launch_bounds__(256) pack_real_kernel(const cplx* __restrict__ src, double* dst,
+                                                        int64_t n) {
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n;
+       r += (int64_t)gridDim.x * blockDim.x)
+    dst[r] = src[r].x;
+}
+__global__ void __launch_bounds__(256) unpack_real_kernel(const double* __restrict__ src, cplx* dst,
+                                                          int64_t n, double scale) {
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n;
+       r += (int64_t)gridDim.x * blockDim.x)
+    dst[r] = make_double2(src[r] * scale, 0.0);
+}
+cudaError_t launch_pack_real(const cplx* src, double* dst, int64_t n, int num_sms, cudaStream_t st) {
+  int64_t grid = (n + 255) / 256;
+  if (grid > (int64_t)num_sms * 8) grid = (int64_t)num_sms * 8;
+  if (grid < 1) grid = 1;
+  pack_real_kernel<<<(int)grid, 256, 0, st>>>(src, dst, n);
+  return cudaGetLastError();
+}
+cudaError_t launch_unpack_real(const double* src, cplx* dst, int64_t n, double scale, int num_sms,
+                               cudaStream_t st) {
+  int64_t grid = (n + 255) / 256;
+  if (grid > (int64_t)num_sms * 8) grid = (int64_t)num_sms * 8;
+  if (grid < 1) grid = 1;
+  unpack_real_kernel<<<(int)grid, 256, 0, st>>>(src, dst, n, scale);
+  return cudaGetLastError();
+}
+
 __global__ void reset_scale_kernel(double* scale, int col0, int ncols) {
   const int i = threadIdx.x;
   if (i < ncols) scale[col0 + i] = 1.0;

@@ -134,6 +134,11 @@ struct ab200_solver {
   // DGKS history: did the second round run on most steps of the last expansion?  Decides
   // between the 3-sweep schedule (pass 1, fused, pass 2) and the 2(+2)-sweep one.
   bool dgks_hot = false;
+  // Real storage: while A is float64 and every column uploaded / every Q applied so far had zero
+  // imaginary parts, the basis is provably real and is kept as float64 (half the bytes, bit-
+  // identical real parts).  The first complex input converts it in place, once.
+  bool real_mode = true;
+  bool pristine = true;   // no column has been written yet
 };
 
 static cudaEvent_t get_event(ab200_solver* s) {
@@ -236,13 +241,40 @@ __global__ void set_scale_kernel(double* scale, int col0, int ncols, double v) {
   for (int i = threadIdx.x; i < ncols; i += blockDim.x) scale[col0 + i] = v;
 }
 
+static inline void* col_ptr(ab200_solver* s, int j) {
+  return s->real_mode ? static_cast<void*>(reinterpret_cast<double*>(s->V) + (size_t)j * s->ld)
+                      : static_cast<void*>(s->V + (size_t)j * s->ld);
+}
+static inline double elem_bytes(const ab200_solver* s) { return s->real_mode ? 8.0 : 16.0; }
+
+// real -> complex storage, in place, columns from the highest down (the complex image of
+// column i >= 1 lies beyond its real image and only covers real columns already converted;
+// column 0 goes through the scratch vector)
+static int switch_to_complex(ab200_solver* s) {
+  if (!s->real_mode) return AB200_OK;
+  if (!s->pristine) {
+    double* vr = reinterpret_cast<double*>(s->V);
+    for (int i = s->max_dim; i >= 1; --i)
+      CU(launch_unpack_real(vr + (size_t)i * s->ld, s->V + (size_t)i * s->ld, s->n, 1.0, s->num_sms,
+                            s->stream));
+    CU(cudaMemcpyAsync(s->wtmp, vr, sizeof(double) * (size_t)s->n, cudaMemcpyDeviceToDevice,
+                       s->stream));
+    CU(launch_unpack_real(reinterpret_cast<const double*>(s->wtmp), s->V, s->n, 1.0, s->num_sms,
+                          s->stream));
+    s->st.kernel_launches += s->max_dim + 1;
+  }
+  s->real_mode = false;
+  return AB200_OK;
+}
+
 static OrthoArgs make_ortho_args(ab200_solver* s, cplx* w, int ncols, int j, double tol, double eta,
                                  cplx* hcol, int finalize) {
   OrthoArgs a;
   a.U = s->V;
   a.w = w;
-  a.n = s->n;
-  a.ld = s->ld;
+  a.real = s->real_mode ? 1 : 0;
+  a.n = s->real_mode ? (s->n + 1) / 2 : s->n;
+  a.ld = s->real_mode ? s->ld / 2 : s->ld;
   a.ncols = ncols;
   a.j = j;
   a.round = 1;
@@ -265,7 +297,7 @@ static OrthoArgs make_ortho_args(ab200_solver* s, cplx* w, int ncols, int j, dou
 
 // enqueue one orthogonalisation (both possible rounds) of w against U[:, :ncols]
 static int enqueue_ortho(ab200_solver* s, OrthoArgs a, int ortho_kind) {
-  const double nb = 16.0 * (double)s->n;
+  const double nb = elem_bytes(s) * (double)s->n;
   const int c = a.ncols;
   const bool fuse = s->opt_ortho_variant == 0 ? s->dgks_hot : s->opt_ortho_variant != 1;
   if (ortho_kind == AB200_ORTHO_CGS2 && fuse) {
@@ -384,7 +416,7 @@ int ab200_create(ab200_solver** out, int device, int64_t n_global, int64_t row0,
   s->row0 = row0;
   s->n = nrows_local;
   s->n_local_cols = nrows_local;
-  s->ld = (nrows_local + 7) / 8 * 8;  // columns start on 128-byte lines
+  s->ld = (nrows_local + 15) / 16 * 16;  // columns start on 128-byte lines in both storage modes
   s->max_dim = max_dim;
   s->grid_cap = s->num_sms * 8;
   const int md1 = max_dim + 1;
@@ -449,6 +481,10 @@ int ab200_set_csr(ab200_solver* s, const void* indptr, int indptr_bits, const in
           (long long)first, (long long)last, (long long)nnz);
   CU(cudaSetDevice(s->device));
   CU(cudaStreamSynchronize(s->stream));
+  if (value_kind == AB200_C128) {
+    int rc = switch_to_complex(s);
+    if (rc != AB200_OK) return rc;
+  }
   cudaFree(s->indptr), cudaFree(s->indices), cudaFree(s->values), cudaFree(s->rowblk);
   s->indptr = s->indices = nullptr, s->values = nullptr, s->rowblk = nullptr;
   s->nnz = -1;
@@ -502,9 +538,36 @@ int ab200_set_columns(ab200_solver* s, int col0, int ncols, const double* host, 
           col0, col0 + ncols, s->max_dim + 1);
   REQUIRE(ld_host >= s->n, "ld_host < nrows_local");
   CU(cudaSetDevice(s->device));
-  CU(cudaMemcpy2DAsync(s->V + (size_t)col0 * s->ld, sizeof(cplx) * s->ld, host,
-                       sizeof(cplx) * ld_host, sizeof(cplx) * s->n, ncols, cudaMemcpyHostToDevice,
-                       s->stream));
+  if (s->real_mode) {
+    // stay real only if every imaginary part is exactly zero
+    bool all_real = true;
+    for (int c = 0; c < ncols && all_real; ++c) {
+      const double* col = host + 2 * (size_t)c * ld_host;
+      for (int64_t r = 0; r < s->n; ++r)
+        if (col[2 * r + 1] != 0.0) {
+          all_real = false;
+          break;
+        }
+    }
+    if (!all_real) {
+      int rc = switch_to_complex(s);
+      if (rc != AB200_OK) return rc;
+    }
+  }
+  if (s->real_mode) {
+    for (int c = 0; c < ncols; ++c) {
+      CU(cudaMemcpyAsync(s->wtmp, host + 2 * (size_t)c * ld_host, sizeof(cplx) * (size_t)s->n,
+                         cudaMemcpyHostToDevice, s->stream));
+      CU(launch_pack_real(s->wtmp, static_cast<double*>(col_ptr(s, col0 + c)), s->n, s->num_sms,
+                          s->stream));
+      s->st.kernel_launches += 1;
+    }
+  } else {
+    CU(cudaMemcpy2DAsync(s->V + (size_t)col0 * s->ld, sizeof(cplx) * s->ld, host,
+                         sizeof(cplx) * ld_host, sizeof(cplx) * s->n, ncols,
+                         cudaMemcpyHostToDevice, s->stream));
+  }
+  s->pristine = false;
   set_scale_kernel<<<1, 128, 0, s->stream>>>(s->scale, col0, ncols, 1.0);
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(s->stream));
@@ -518,6 +581,18 @@ int ab200_get_columns(ab200_solver* s, int col0, int ncols, double* host, int64_
           col0, col0 + ncols, s->max_dim + 1);
   REQUIRE(ld_host >= s->n, "ld_host < nrows_local");
   CU(cudaSetDevice(s->device));
+  if (s->real_mode) {
+    // expand column by column through the scratch vector, lazy scale applied on the way out
+    for (int c = 0; c < ncols; ++c) {
+      CU(launch_unpack_real(static_cast<const double*>(col_ptr(s, col0 + c)), s->wtmp, s->n,
+                            s->h_scale[col0 + c], s->num_sms, s->stream));
+      s->st.kernel_launches += 1;
+      CU(cudaMemcpyAsync(host + 2 * (size_t)c * ld_host, s->wtmp, sizeof(cplx) * (size_t)s->n,
+                         cudaMemcpyDeviceToHost, s->stream));
+    }
+    CU(cudaStreamSynchronize(s->stream));
+    return AB200_OK;
+  }
   // apply the lazy scales in place first (a no-op for columns whose scale is 1)
   CU(launch_materialize(s->V, s->n, s->ld, col0, ncols, s->scale, s->num_sms, s->stream));
   s->st.kernel_launches += 2;
@@ -529,7 +604,7 @@ int ab200_get_columns(ab200_solver* s, int col0, int ncols, double* host, int64_
   return AB200_OK;
 }
 
-static int enqueue_spmv(ab200_solver* s, const cplx* x, cplx* y, const double* xscale, int step,
+static int enqueue_spmv(ab200_solver* s, const void* x, void* y, const double* xscale, int step,
                         bool in_expand) {
   SpmvArgs a;
   a.indptr = s->indptr;
@@ -545,17 +620,20 @@ static int enqueue_spmv(ab200_solver* s, const cplx* x, cplx* y, const double* x
   a.nblocks = s->nblk;
   a.tile = s->tile;
   a.threads = s->spmv_threads;
+  a.real = (in_expand && s->real_mode) ? 1 : 0;
   a.long_rows = s->max_row_len > 16 ? 1 : 0;
   a.ctl = in_expand ? s->ctl : nullptr;
   const double sv = s->value_kind == AB200_F64 ? 8.0 : 16.0;
-  const double bytes = (double)s->nnz * (sv + 4.0) + (double)s->n * (s->indptr_bits / 8 + 32.0) +
-                       32.0 * (double)s->nghost;
+  const double eb = a.real ? 8.0 : 16.0;
+  const double bytes = (double)s->nnz * (sv + 4.0) + (double)s->n * (s->indptr_bits / 8 + 2.0 * eb) +
+                       2.0 * eb * (double)s->nghost;
   LaunchScope ls(s, K_SPMV, step, 0, bytes);
   if (s->push) {
     if (!in_expand) return set_err(AB200_ESTATE, "halo SpMV is only available inside ab200_expand");
     s->hseq += 1;
     HaloPushArgs p;
-    p.U_col = x;
+    p.U_col = static_cast<const cplx*>(x);
+    p.real = a.real;
     p.send_idx = s->send_idx;
     for (int r = 0; r <= kMaxRanks; ++r) p.send_ptr[r] = s->send_ptr[r];
     unsigned need = 0;
@@ -586,6 +664,7 @@ static int enqueue_spmv(ab200_solver* s, const cplx* x, cplx* y, const double* x
     h.ghost = s->ghost;
     h.nghost = s->nghost;
     h.col = step;
+    h.real = a.real;
     h.nranks = s->nranks;
     h.ctl = s->ctl;
     CU(launch_halo_gather(h, s->num_sms, s->stream));
@@ -606,6 +685,7 @@ int ab200_expand(ab200_solver* s, int start_dim, int end_dim, double tol, double
           ortho_kind);
   if (s->nnz < 0) return set_err(AB200_ESTATE, "ab200_expand called before ab200_set_csr");
   CU(cudaSetDevice(s->device));
+  s->pristine = false;
   const int md1 = s->max_dim + 1;
   init_ctl_kernel<<<1, 32, 0, s->stream>>>(s->ctl, nullptr, 0, false);
   CU(cudaGetLastError());
@@ -616,11 +696,12 @@ int ab200_expand(ab200_solver* s, int start_dim, int end_dim, double tol, double
     s->st.kernel_launches += 1;
   }
   for (int j = start_dim; j < end_dim; ++j) {
-    cplx* x = s->V + (size_t)j * s->ld;
-    cplx* w = s->V + (size_t)(j + 1) * s->ld;
+    void* x = col_ptr(s, j);
+    void* w = col_ptr(s, j + 1);
     int rc = enqueue_spmv(s, x, w, s->scale + j, j, true);  // decomposition.py:57-58
     if (rc != AB200_OK) return rc;
-    OrthoArgs a = make_ortho_args(s, w, j + 1, j, tol, eta, s->Hdev + (size_t)j * md1, 1);
+    OrthoArgs a = make_ortho_args(s, static_cast<cplx*>(w), j + 1, j, tol, eta,
+                                  s->Hdev + (size_t)j * md1, 1);
     a.step_flag = s->step_round2 + j;
     rc = enqueue_ortho(s, a, ortho_kind);  // decomposition.py:60
     if (rc != AB200_OK) return rc;
@@ -667,8 +748,21 @@ int ab200_restart(ab200_solver* s, const double* q, int64_t ldq, int m, int p) {
           m, s->max_dim);
   REQUIRE(ldq >= m, "ldq < m");
   CU(cudaSetDevice(s->device));
-  // fold the lazy column scales into the rows of Q:  V_i = scale[i] U_i
   const cplx* qh = reinterpret_cast<const cplx*>(q);
+  if (s->real_mode) {
+    bool q_real = true;
+    for (int k = 0; k < p && q_real; ++k)
+      for (int i = 0; i < m; ++i)
+        if (qh[(size_t)k * ldq + i].y != 0.0) {
+          q_real = false;
+          break;
+        }
+    if (!q_real) {  // complex Schur vectors: the basis becomes complex from here on
+      int rc = switch_to_complex(s);
+      if (rc != AB200_OK) return rc;
+    }
+  }
+  // fold the lazy column scales into the rows of Q:  V_i = scale[i] U_i
   for (int i = 0; i < m; ++i)
     for (int k = 0; k < p; ++k) {
       const cplx v = qh[(size_t)k * ldq + i];
@@ -678,14 +772,15 @@ int ab200_restart(ab200_solver* s, const double* q, int64_t ldq, int m, int p) {
                      s->stream));
   RestartArgs a;
   a.U = s->V;
-  a.n = s->n;
-  a.ld = s->ld;
+  a.real = s->real_mode ? 1 : 0;
+  a.n = s->real_mode ? (s->n + 1) / 2 : s->n;
+  a.ld = s->real_mode ? s->ld / 2 : s->ld;
   a.m = m;
   a.p = p;
   a.q = s->qdev;
   a.scale_m = s->h_scale[m];
   {
-    LaunchScope ls(s, K_RESTART, -1, 0, 16.0 * (double)s->n * (m + p + 2));
+    LaunchScope ls(s, K_RESTART, -1, 0, elem_bytes(s) * (double)s->n * (m + p + 2));
     CU(launch_restart(a, s->num_sms, s->stream, s->opt_restart_variant));
   }
   set_scale_kernel<<<1, 128, 0, s->stream>>>(s->scale, 0, p + 1, 1.0);
@@ -725,6 +820,10 @@ int ab200_ortho(ab200_solver* s, int ncols, double* w_host, double* h_host, doub
   REQUIRE(ortho_kind == AB200_ORTHO_CGS2 || ortho_kind == AB200_ORTHO_MGS, "bad ortho_kind %d",
           ortho_kind);
   CU(cudaSetDevice(s->device));
+  {  // the stand-alone plug takes an arbitrary complex w: work on complex storage
+    int rc = switch_to_complex(s);
+    if (rc != AB200_OK) return rc;
+  }
   CU(cudaMemcpyAsync(s->wtmp, w_host, sizeof(cplx) * (size_t)s->n, cudaMemcpyHostToDevice,
                      s->stream));
   CU(cudaMemsetAsync(s->hscratch, 0, sizeof(cplx) * (s->max_dim + 2), s->stream));
@@ -952,6 +1051,7 @@ int ab200_reset_stats(ab200_solver* s) {
 int ab200_get_stats(ab200_solver* s, ab200_stats* out) {
   REQUIRE(s != nullptr && out != nullptr, "null argument");
   *out = s->st;
+  out->real_storage = s->real_mode ? 1 : 0;
   return AB200_OK;
 }
 
@@ -994,7 +1094,17 @@ int ab200_set_option(ab200_solver* s, const char* key, int64_t value) {
     s->opt_ortho_variant = (int)value;
   else if (!strcmp(key, "fused_ct"))
     s->opt_fused_ct = (int)value;
-  else if (!strcmp(key, "spmv_threads"))
+  else if (!strcmp(key, "real_mode")) {
+    if (value == 0) {
+      CU(cudaSetDevice(s->device));
+      int rc = switch_to_complex(s);
+      if (rc != AB200_OK) return rc;
+    } else if (!s->pristine && !s->real_mode) {
+      return set_err(AB200_ESTATE, "real storage can only be chosen before any column is written");
+    } else if (s->pristine) {
+      s->real_mode = true;
+    }
+  } else if (!strcmp(key, "spmv_threads"))
     s->opt_spmv_threads = (int)value;
   else if (!strcmp(key, "spmv_tile"))
     s->opt_spmv_tile = (int)value;

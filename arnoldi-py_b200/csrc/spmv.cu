@@ -44,6 +44,18 @@ struct ValOps<cplx> {
 __device__ __forceinline__ cplx cadd_rn(cplx a, cplx b) {
   return make_double2(__dadd_rn(a.x, b.x), __dadd_rn(a.y, b.y));
 }
+// real-storage mode: x and y are float64 (A must be float64 too); same operation order, so the
+// result equals the real part of what the complex path computes, bit for bit
+__device__ __forceinline__ double cadd_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double vmul(double a, double x) { return __dmul_rn(a, x); }
+__device__ __forceinline__ cplx vmul(double a, cplx x) { return ValOps<double>::mul(a, x); }
+__device__ __forceinline__ cplx vmul(cplx a, cplx x) { return ValOps<cplx>::mul(a, x); }
+__device__ __forceinline__ double vmul(cplx a, double x) { return 0.0 * a.x * x; }  // never used
+__device__ __forceinline__ double ld_ro(const double* p) { return __ldg(p); }
+__device__ __forceinline__ double cscale(double a, double s) { return a * s; }
+template <typename XT> __device__ __forceinline__ XT xzero();
+template <> __device__ __forceinline__ double xzero<double>() { return 0.0; }
+template <> __device__ __forceinline__ cplx xzero<cplx>() { return make_double2(0.0, 0.0); }
 
 template <typename IdxT>
 __global__ void spmv_maxrow_kernel(const IdxT* __restrict__ indptr, int64_t n, int* __restrict__ out) {
@@ -85,7 +97,7 @@ __global__ void spmv_plan_kernel(const IdxT* __restrict__ indptr, int64_t n, int
 
 // LONG = false: the matrix has no row longer than kShortRow, the warp-per-row machinery is
 // compiled out (lean kernel for banded operators: mark, Laplacians).
-template <typename IdxT, typename ValT, int kSpmvThreads, bool LONG>
+template <typename IdxT, typename ValT, typename XT, int kSpmvThreads, bool LONG>
 __global__ void __launch_bounds__(kSpmvThreads) spmv_tile_kernel(SpmvArgs a) {
   if (a.ctl != nullptr && a.ctl->stop) return;
 
@@ -99,8 +111,9 @@ __global__ void __launch_bounds__(kSpmvThreads) spmv_tile_kernel(SpmvArgs a) {
   const IdxT* __restrict__ indptr = static_cast<const IdxT*>(a.indptr);
   const ValT* __restrict__ values = static_cast<const ValT*>(a.values);
   const int32_t* __restrict__ indices = a.indices;
-  const cplx* __restrict__ x = a.x;
-  const cplx* __restrict__ ghost = a.ghost;
+  const XT* __restrict__ x = static_cast<const XT*>(a.x);
+  const XT* __restrict__ ghost = static_cast<const XT*>(a.ghost);
+  XT* __restrict__ yout = static_cast<XT*>(a.y);
   const int64_t nloc = a.n_local_cols;
   const double xs = a.xscale ? *a.xscale : 1.0;
   const int tid = threadIdx.x;
@@ -150,28 +163,28 @@ __global__ void __launch_bounds__(kSpmvThreads) spmv_tile_kernel(SpmvArgs a) {
           s_long_row[slot] = row;
           continue;
         }
-        cplx acc = (rs < cs) ? a.y[row] : make_double2(0.0, 0.0);
+        XT acc = (rs < cs) ? yout[row] : xzero<XT>();
         int k = (int)(lo - ca);
         const int kend = (int)(hi - ca);
 
         for (; k + 4 <= kend; k += 4) {
-          cplx xv[4];
+          XT xv[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const int64_t col = scol[k + u];
             xv[u] = (col < nloc) ? ld_ro(x + col) : ld_ro(ghost + (col - nloc));
           }
 #pragma unroll
-          for (int u = 0; u < 4; ++u) acc = cadd_rn(acc, ValOps<ValT>::mul(sval[k + u], xv[u]));
+          for (int u = 0; u < 4; ++u) acc = cadd_rn(acc, vmul(sval[k + u], xv[u]));
         }
 
         for (; k < kend; ++k) {
           const int64_t col = scol[k];
-          const cplx xv = (col < nloc) ? ld_ro(x + col) : ld_ro(ghost + (col - nloc));
-          acc = cadd_rn(acc, ValOps<ValT>::mul(sval[k], xv));
+          const XT xv = (col < nloc) ? ld_ro(x + col) : ld_ro(ghost + (col - nloc));
+          acc = cadd_rn(acc, vmul(sval[k], xv));
         }
         if (re <= ce) acc = cscale(acc, xs);  // row complete: apply the lazy scale of x
-        a.y[row] = acc;
+        yout[row] = acc;
       }
       __syncthreads();
       // ---- longer segments: one warp per row, lanes stride the segment, fixed-order butterfly
@@ -181,17 +194,17 @@ __global__ void __launch_bounds__(kSpmvThreads) spmv_tile_kernel(SpmvArgs a) {
         const int64_t rs = (int64_t)indptr[row], re = (int64_t)indptr[row + 1];
         const int64_t lo = rs > cs ? rs : cs;
         const int64_t hi = re < ce ? re : ce;
-        cplx acc = make_double2(0.0, 0.0);
+        XT acc = xzero<XT>();
         for (int k = (int)(lo - ca) + (tid & 31); k < (int)(hi - ca); k += kWarp) {
           const int64_t col = scol[k];
-          const cplx xv = (col < nloc) ? ld_ro(x + col) : ld_ro(ghost + (col - nloc));
-          acc = cadd_rn(acc, ValOps<ValT>::mul(sval[k], xv));
+          const XT xv = (col < nloc) ? ld_ro(x + col) : ld_ro(ghost + (col - nloc));
+          acc = cadd_rn(acc, vmul(sval[k], xv));
         }
         acc = warp_sum(acc);
         if ((tid & 31) == 0) {
-          cplx t = (rs < cs) ? cadd_rn(a.y[row], acc) : acc;
+          XT t = (rs < cs) ? cadd_rn(yout[row], acc) : acc;
           if (re <= ce) t = cscale(t, xs);
-          a.y[row] = t;
+          yout[row] = t;
         }
       }
     }
@@ -223,32 +236,44 @@ cudaError_t launch_spmv_plan(const void* indptr, int indptr_bits, int64_t n, int
   return cudaGetLastError();
 }
 
-template <typename IdxT, typename ValT, int THREADS, bool LONG>
+template <typename IdxT, typename ValT, typename XT, int THREADS, bool LONG>
 static cudaError_t launch_spmv_ttl(const SpmvArgs& a, cudaStream_t st) {
   const size_t smem = (size_t)(a.tile + 4) * (sizeof(ValT) + sizeof(int32_t)) + 16 +
                       sizeof(int64_t) * (size_t)(a.tile / 16 + 2);
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(spmv_tile_kernel<IdxT, ValT, THREADS, LONG>,
+    cudaFuncSetAttribute(spmv_tile_kernel<IdxT, ValT, XT, THREADS, LONG>,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     attr_done = true;
   }
   const int grid = a.nblocks;  // one tile per block; blocks are small and many per SM
-  spmv_tile_kernel<IdxT, ValT, THREADS, LONG><<<grid, THREADS, smem, st>>>(a);
+  spmv_tile_kernel<IdxT, ValT, XT, THREADS, LONG><<<grid, THREADS, smem, st>>>(a);
   return cudaGetLastError();
 }
-template <typename IdxT, typename ValT, int THREADS>
+template <typename IdxT, typename ValT, typename XT, int THREADS>
 static cudaError_t launch_spmv_tt(const SpmvArgs& a, cudaStream_t st) {
-  return a.long_rows ? launch_spmv_ttl<IdxT, ValT, THREADS, true>(a, st)
-                     : launch_spmv_ttl<IdxT, ValT, THREADS, false>(a, st);
+  return a.long_rows ? launch_spmv_ttl<IdxT, ValT, XT, THREADS, true>(a, st)
+                     : launch_spmv_ttl<IdxT, ValT, XT, THREADS, false>(a, st);
+}
+template <typename IdxT, typename ValT, typename XT>
+static cudaError_t launch_spmv_x(const SpmvArgs& a, cudaStream_t st) {
+  return a.threads == 128 ? launch_spmv_tt<IdxT, ValT, XT, 128>(a, st)
+                          : launch_spmv_tt<IdxT, ValT, XT, 256>(a, st);
 }
 template <typename IdxT, typename ValT>
 static cudaError_t launch_spmv_t(const SpmvArgs& a, cudaStream_t st) {
-  return a.threads == 128 ? launch_spmv_tt<IdxT, ValT, 128>(a, st)
-                          : launch_spmv_tt<IdxT, ValT, 256>(a, st);
+  return launch_spmv_x<IdxT, ValT, cplx>(a, st);
+}
+template <typename IdxT>
+static cudaError_t launch_spmv_real(const SpmvArgs& a, cudaStream_t st) {
+  return launch_spmv_x<IdxT, double, double>(a, st);
 }
 
 cudaError_t launch_spmv(const SpmvArgs& a, int indptr_bits, int value_kind, cudaStream_t st) {
+  if (a.real) {
+    if (value_kind != 0) return cudaErrorInvalidValue;  // real vectors need a float64 matrix
+    return indptr_bits == 32 ? launch_spmv_real<int32_t>(a, st) : launch_spmv_real<int64_t>(a, st);
+  }
   if (indptr_bits == 32) {
     return value_kind == 0 ? launch_spmv_t<int32_t, double>(a, st)
                            : launch_spmv_t<int32_t, cplx>(a, st);

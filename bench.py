@@ -220,6 +220,13 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def storage_note(st):
+    """complex128 arithmetic as in the reference; while A, v0 and every Schur basis applied are
+    real the imaginary parts are exactly zero and the device holds the basis as float64."""
+    return ("c128 (basis stored f64: provably real on this operator, results identical)"
+            if st.get("real_storage") else "c128")
+
+
 def workload_config():
     return {"workload": f"lap2d({GRID_FULL}) n={GRID_FULL**2} nnz={5*GRID_FULL**2-4*GRID_FULL} "
                         f"float64 CSR, K={NEV}, max_dim={MAX_DIM}, p={P}, LR, tol={TOL}, seed 0",
@@ -255,6 +262,8 @@ def run_b200(args):
     H = np.zeros((MAX_DIM + 1, MAX_DIM), np.complex128)
 
     dev = DeviceSolver(n, MAX_DIM, device=local)
+    if args.complex_storage:
+        dev.set_option("real_mode", 0)
     dev.set_timing(True)
     dev.set_csr(A.indptr, A.indices, A.data)
     dev.set_columns(0, v0)
@@ -332,7 +341,8 @@ def run_b200(args):
             t0 = time.perf_counter()
             Q, T, hist = partial_schur(Ap, NEV, max_dim=MAX_DIM, stopping_criterion=TOL,
                                        sort_function=arg_largest_real, max_restarts=restarts,
-                                       raise_on_no_convergence=False, stats=stats, device=local)
+                                       raise_on_no_convergence=False, stats=stats, device=local,
+                                       real_storage=not args.complex_storage)
             dt = time.perf_counter() - t0
             if rep > 0:
                 times.append(dt)
@@ -353,8 +363,9 @@ def run_b200(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "c128",
-        "data": "synthetic", "config": workload_config() if grid == GRID_FULL else
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": storage_note(st), "data": "synthetic",
+        "config": workload_config() if grid == GRID_FULL else
         {"workload": f"lap2d({grid}) REDUCED (not config 2)"},
         "wall_ms_per_step": 1e3 * wall / args.steps,
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
@@ -409,6 +420,8 @@ def run_b200_multi(args, rank, world, local):
     H = np.zeros((MAX_DIM + 1, MAX_DIM), np.complex128)
 
     dev = DeviceSolver(n, MAX_DIM, device=local, row0=r0, nrows_local=r1 - r0)
+    if args.complex_storage:
+        dev.set_option("real_mode", 0)
     dev.set_timing(True)
     dev.connect(comm, part)
     dev.set_halo(plan.ghost_cols)
@@ -487,7 +500,8 @@ def run_b200_multi(args, rank, world, local):
             t0 = time.perf_counter()
             partial_schur(A, NEV, max_dim=MAX_DIM, stopping_criterion=TOL,
                           sort_function=arg_largest_real, max_restarts=restarts,
-                          raise_on_no_convergence=False, stats=stats, device=local, comm=comm)
+                          raise_on_no_convergence=False, stats=stats, device=local, comm=comm,
+                          real_storage=not args.complex_storage)
             dt = comm.max_float(time.perf_counter() - t0)
             if rep > 0:
                 times.append(dt)
@@ -504,8 +518,9 @@ def run_b200_multi(args, rank, world, local):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_max / args.steps,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "c128",
-            "data": "synthetic", "config": dict(workload_config(), parallelism=f"block-row x{world}")
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": storage_note(st), "data": "synthetic",
+            "config": dict(workload_config(), parallelism=f"block-row x{world}")
             if grid == GRID_FULL else {"workload": f"lap2d({grid}) REDUCED (not config 2)"},
             "wall_ms_per_step": 1e3 * wall_max / args.steps,
             "roofline": roofline, "cpu_baseline": None, "e2e": e2e,
@@ -526,6 +541,8 @@ def main():
     ap.add_argument("--e2e-restarts", type=int, default=24)
     ap.add_argument("--e2e-reps", type=int, default=1)
     ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--complex-storage", action="store_true",
+                    help="keep the basis as complex128 even while it is provably real")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

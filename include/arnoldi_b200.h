@@ -69,6 +69,7 @@ typedef struct ab200_stats {
   int64_t ortho_rounds;    /* CGS/MGS rounds executed (1 or 2 per step)     */
   int64_t second_rounds;   /* steps where the DGKS test fired               */
   int64_t kernel_launches; /* every kernel this library launched            */
+  int64_t real_storage;    /* 1 while the basis is held as float64 (provably real) */
 } ab200_stats;
 
 int ab200_abi_version(void);
@@ -178,6 +179,8 @@ int ab200_timer_stop(ab200_solver *s, double *elapsed_ms);
  *                     2 = always fused (register loads), 3 = always fused (cp.async staging)
  *   "fused_ct"        column-tile width of the fused sweep (1..8)
  *   "restart_variant" outputs per warp of the restart kernel (4, 8, 16)
+ *   "real_mode"       0 = keep the basis as complex128 from the start (default: float64
+ *                     storage while A, v0 and every Q applied are real -- see DESIGN.md)
  *   "grid_mult"       resident blocks per SM for the orthogonalisation kernels
  *   "spmv_tile"       non-zeros staged per SpMV block    } take effect at the next
  *   "spmv_threads"    SpMV block size, 128 or 256        } ab200_set_csr */

@@ -252,3 +252,40 @@ def test_krylov_schur_relations_at_one_million_rows(gpu):
         check()
         st = dev.stats()
         assert st["arnoldi_steps"] == m + (m - p)
+
+
+def test_real_storage_is_lossless(gpu, golden):
+    """float64 storage of a provably real basis: same Ritz values, restart counts and residuals
+    as forced complex128 storage; symmetric real operator stays real to the end, a nonsymmetric
+    one turns complex at its first restart; odd n (pair padding)."""
+    from arnoldi_b200 import partial_schur
+    from arnoldi_b200.matrices import lap2d as lap2d_direct, mark
+    from arnoldi_b200.utils import arg_largest_real
+    for A, nev, md, stays_real in ((lap2d_direct(31), 6, 24, True), (mark(30), 5, 20, False),
+                                   (lap2d_direct(64), 10, 40, True)):
+        out = []
+        for real in (True, False):
+            np.random.seed(0)
+            stats = {}
+            Q, T, hist = partial_schur(A, nev, max_dim=md, stopping_criterion=1e-8,
+                                       max_restarts=2000, sort_function=arg_largest_real,
+                                       stats=stats, real_storage=real)
+            out.append((Q, T, hist, stats))
+            assert stats["real_storage"] == (1 if (real and stays_real) else 0)
+            res = np.linalg.norm(A @ Q - Q @ T, axis=0)
+            assert res.max() < 1e-7
+        (Qr, Tr, hr, _), (Qc, Tc, hc, _) = out
+        assert abs(int(hr.restarts[0]) - int(hc.restarts[0])) <= 2
+        if int(hr.restarts[0]) == int(hc.restarts[0]):
+            np.testing.assert_allclose(np.diag(Tr), np.diag(Tc), rtol=1e-10)
+        if stays_real:
+            assert not Qr.imag.any() and not Tr.imag.any()
+    # against the reference's record for the Laplacian, real storage
+    g = golden("solves")
+    np.random.seed(0)
+    stats = {}
+    A = lap2d(64)
+    Q, T, hist = partial_schur(A, 10, max_dim=40, stopping_criterion=1e-8, max_restarts=1000,
+                               sort_function=arg_largest_real, stats=stats)
+    _check_against_record(A, Q, T, hist, stats, g, "lap2d64_s0", 1e-8, restart_slack=2)
+    assert stats["real_storage"] == 1

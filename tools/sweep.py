@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--max-dim", type=int, default=40)
     ap.add_argument("--cycles", type=int, default=2)
     ap.add_argument("--ortho", default="cgs2")
+    ap.add_argument("--complex-storage", action="store_true")
     ap.add_argument("sets", nargs="*", default=[""])
     args = ap.parse_args()
     from arnoldi_b200 import _lib
@@ -42,6 +43,8 @@ def main():
     v0 = rand_normalized_vector(n, np.complex128)
     H = np.zeros((m + 1, m), np.complex128)
     dev = DeviceSolver(n, m)
+    if args.complex_storage:
+        dev.set_option("real_mode", 0)
     dev.set_timing(True)
     dev.set_csr(A.indptr, A.indices, A.data)
     dev.set_columns(0, v0)
@@ -79,7 +82,7 @@ def main():
             cycle()
         ms = dev.timer_stop()
         st = dev.stats()
-        out = {"opts": spec, "ms_per_cycle": ms / args.cycles}
+        out = {"opts": spec, "ms_per_cycle": ms / args.cycles, "real_storage": st["real_storage"]}
         for key in ("spmv", "ortho_pass1", "ortho_fused", "ortho_pass2", "mgs", "restart"):
             if st[key + "_launches"]:
                 out[key] = {"avg_ms": round(st[key + "_ms"] / st[key + "_launches"], 4),
