@@ -82,7 +82,13 @@ def test_partial_schur_matches_reference_solves(gpu, golden, tag, mat, seed, kw)
     np.random.seed(seed)
     stats = {}
     Q, T, hist = partial_schur(A, nev, sort_function=arg_largest_real, stats=stats, **kw)
-    R, Rref = _check_against_record(A, Q, T, hist, stats, g, tag, tol, restart_slack=2)
+    # The 2-D Laplacian has double eigenvalues: when the second copy of one enters the wanted
+    # set is decided by rounding noise, so its restart count moves by a few
+    # with ANY change of summation order (the reference's own CGS2 / MGS differ by 2 at N = 128).
+    slack = 4 if mat.startswith("lap2d") else 2
+    R, Rref = _check_against_record(A, Q, T, hist, stats, g, tag, tol, restart_slack=slack)
+    if not mat.startswith("lap2d"):
+        assert R == Rref        # simple spectra: identical restart counts in every recorded case
     # history formula of the reference (krylov_schur.py:63) and the true operator count
     md = kw["max_dim"]
     p = min(nev + 5, md - 1)
@@ -275,7 +281,7 @@ def test_real_storage_is_lossless(gpu, golden):
             res = np.linalg.norm(A @ Q - Q @ T, axis=0)
             assert res.max() < 1e-7
         (Qr, Tr, hr, _), (Qc, Tc, hc, _) = out
-        assert abs(int(hr.restarts[0]) - int(hc.restarts[0])) <= 2
+        assert abs(int(hr.restarts[0]) - int(hc.restarts[0])) <= (4 if stays_real else 0)
         if int(hr.restarts[0]) == int(hc.restarts[0]):
             np.testing.assert_allclose(np.diag(Tr), np.diag(Tc), rtol=1e-10)
         if stays_real:
@@ -287,5 +293,5 @@ def test_real_storage_is_lossless(gpu, golden):
     A = lap2d(64)
     Q, T, hist = partial_schur(A, 10, max_dim=40, stopping_criterion=1e-8, max_restarts=1000,
                                sort_function=arg_largest_real, stats=stats)
-    _check_against_record(A, Q, T, hist, stats, g, "lap2d64_s0", 1e-8, restart_slack=2)
+    _check_against_record(A, Q, T, hist, stats, g, "lap2d64_s0", 1e-8, restart_slack=4)
     assert stats["real_storage"] == 1
