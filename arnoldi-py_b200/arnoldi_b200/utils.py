@@ -48,7 +48,15 @@ def ordered_schur(a, output="real", *, sort_function=None):
         raise ValueError("output!='complex' not implemented yet")
     if sort_function is None:
         sort_function = arg_largest_magnitude
-    T, Z = schur(a, output="complex")
+    a = np.asarray(a)
+    if a.dtype.kind == "c" and not np.tril(a, -1).any():
+        # The reference re-factors its input here (utils.py:45) although partial_schur passes
+        # the already-triangular T1 (krylov_schur.py:70).  LAPACK's zgees returns an exactly
+        # triangular input unchanged with Z = I (bit for bit; test_host_logic checks it), so
+        # the call is skipped: 0.3-0.5 ms per restart that the GPUs would spend idle.
+        T, Z = np.array(a, order="F", copy=True), np.eye(a.shape[0], dtype=a.dtype, order="F")
+    else:
+        T, Z = schur(a, output="complex")
     swap = _SWAPPERS[np.result_type(a.dtype, 1j)]
     slots = list(range(T.shape[0]))
     for dest, original in enumerate(sort_function(np.diag(T))):

@@ -748,6 +748,7 @@ int ab200_restart(ab200_solver* s, const double* q, int64_t ldq, int m, int p) {
           m, s->max_dim);
   REQUIRE(ldq >= m, "ldq < m");
   CU(cudaSetDevice(s->device));
+  CU(cudaStreamSynchronize(s->stream));  // the pinned Q staging buffer is free again
   const cplx* qh = reinterpret_cast<const cplx*>(q);
   if (s->real_mode) {
     bool q_real = true;
@@ -786,9 +787,9 @@ int ab200_restart(ab200_solver* s, const double* q, int64_t ldq, int m, int p) {
   set_scale_kernel<<<1, 128, 0, s->stream>>>(s->scale, 0, p + 1, 1.0);
   CU(cudaGetLastError());
   s->st.kernel_launches += 1;
-  CU(cudaStreamSynchronize(s->stream));
+  // no synchronisation here: the host goes on to update H and to enqueue the next expansion
+  // while the update runs (the next call that reads results synchronises)
   for (int i = 0; i <= p; ++i) s->h_scale[i] = 1.0;
-  resolve_pending(s, nullptr);
   return AB200_OK;
 }
 

@@ -140,3 +140,35 @@ def test_powerlaw_generator_is_shardable():
     d = np.sort(A.diagonal())[::-1]
     np.testing.assert_allclose(d[:POWERLAW_TOP], 3.0 + 0.25 * np.arange(POWERLAW_TOP)[::-1])
     assert d[POWERLAW_TOP] <= 2.0
+
+
+def test_ordered_schur_triangular_shortcut_is_exact():
+    """ordered_schur skips LAPACK's zgees when its input is already upper triangular (what
+    partial_schur passes).  That must be bit-identical to calling zgees: zgees maps a triangular
+    matrix to itself with Z = I."""
+    from scipy.linalg import schur
+    from scipy.linalg.lapack import ztrexc
+    from arnoldi_b200.utils import arg_largest_magnitude, arg_largest_real, ordered_schur
+    rng = np.random.default_rng(12)
+    for trial in range(40):
+        m = int(rng.integers(2, 64))
+        if trial % 2:
+            H = np.triu(rng.standard_normal((m, m)) + 1j * rng.standard_normal((m, m)), -1)
+        else:
+            H = np.triu(rng.standard_normal((m, m)), -1).astype(np.complex128)
+        T1, Q1 = schur(H, output="complex")
+        T0, Z0 = schur(T1, output="complex")
+        np.testing.assert_array_equal(T0, T1)
+        np.testing.assert_array_equal(Z0, np.eye(m))
+        for sort in (arg_largest_real, arg_largest_magnitude):
+            # the reference's sequence, spelled out with the zgees call it makes
+            T, Z = T0.copy(), Z0.copy()
+            slots = list(range(m))
+            for dest, original in enumerate(sort(np.diag(T0))):
+                here = slots.index(original)
+                if here != dest:
+                    T, Z, _ = ztrexc(T, Z, here + 1, dest + 1)
+                    slots.insert(dest, slots.pop(here))
+            T2, Z2 = ordered_schur(T1, output="complex", sort_function=sort)
+            np.testing.assert_array_equal(T2, T)
+            np.testing.assert_array_equal(Z2, Z)
