@@ -192,7 +192,7 @@ def partial_schur(
         if not converged and raise_on_no_convergence:
             raise ValueError("Has not converged !")
         lap("host_schur")
-        Qout = dev.get_columns(0, nev)
+        Qout = dev.get_columns(0, nev, pinned=True)
         lap("download_q")
         if multi:
             comm.barrier()   # nobody unmaps while a peer may still be in its last kernel
