@@ -57,12 +57,14 @@ def ordered_schur(a, output="real", *, sort_function=None):
         T, Z = np.array(a, order="F", copy=True), np.eye(a.shape[0], dtype=a.dtype, order="F")
     else:
         T, Z = schur(a, output="complex")
+        T, Z = np.asfortranarray(T), np.asfortranarray(Z)
     swap = _SWAPPERS[np.result_type(a.dtype, 1j)]
     slots = list(range(T.shape[0]))
     for dest, original in enumerate(sort_function(np.diag(T))):
         here = slots.index(original)
         if here == dest:
             continue
-        T, Z, _ = swap(T, Z, here + 1, dest + 1)  # LAPACK is 1-based
+        # T and Z are this function's own Fortran-ordered arrays: let LAPACK work in place
+        T, Z, _ = swap(T, Z, here + 1, dest + 1, overwrite_a=1, overwrite_q=1)  # 1-based
         slots.insert(dest, slots.pop(here))
     return T, Z
