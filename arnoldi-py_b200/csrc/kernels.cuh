@@ -19,6 +19,7 @@ struct OrthoArgs {
   int accumulate;    // h += (round 2) instead of h =
   int finalize;      // write H[j+1, j], scale[j+1], breakdown flag when the step ends
   int grid_cap;      // capacity (in blocks) of the partial buffers
+  int stages;        // cp.async staging depth of the fused sweep (0 = automatic)
   double tol;        // breakdown threshold (absolute, ortho.py:107)
   double eta;        // DGKS factor (ortho.py:101)
   double* scale;     // [max_dim + 1]

@@ -368,7 +368,7 @@ __device__ __forceinline__ void cp_async_wait() {
 // PF = true: the block's NEXT chunk is staged into shared memory with cp.async (LDGSTS,
 // no registers held) while the current one is processed, so requests stay in flight across
 // the block barrier.  PF = false: plain register loads (more blocks per SM instead).
-template <int CT, int R, bool PF, bool REAL>
+template <int CT, int R, bool PF, bool REAL, int S>
 __global__ void __launch_bounds__(CT < 5 ? 256 : 512) cgs_fused_kernel(OrthoArgs a) {
   StepCtl* ctl = a.ctl;
   if (ctl->stop) return;
@@ -382,8 +382,8 @@ __global__ void __launch_bounds__(CT < 5 ? 256 : 512) cgs_fused_kernel(OrthoArgs
   cplx* spart = reinterpret_cast<cplx*>(fused_smem);  // [2][nwarps][ROWS]
   cplx* scoef = spart + 2 * nwarps * ROWS;            // [nwarps * CT]
   cplx* swp = scoef + nwarps * CT;                    // [ROWS]                  w' of the chunk
-  cplx* sw = swp + ROWS;                              // PF: [2][ROWS]           chunk of w
-  cplx* sv = sw + 2 * ROWS;                           // PF: [2][nwarps][CT][ROWS] chunk of U
+  cplx* sw = swp + ROWS;                              // PF: [S][ROWS]           chunk of w
+  cplx* sv = sw + S * ROWS;                           // PF: [S][nwarps][CT][ROWS] chunk of U
   for (int i = threadIdx.x; i < nwarps * CT; i += blockDim.x)
     scoef[i] = i < c ? a.coef[i] : make_double2(0.0, 0.0);
   __syncthreads();
@@ -431,25 +431,36 @@ __global__ void __launch_bounds__(CT < 5 ? 256 : 512) cgs_fused_kernel(OrthoArgs
 
   int buf = 0;
   if (PF) {
-    if ((int64_t)blockIdx.x < nchunks) {
-      if (warp == 0) stage_w(blockIdx.x, 0);
-      stage_v(blockIdx.x, 0);
+    // prologue: S - 1 chunks in flight before the first one is consumed
+#pragma unroll
+    for (int st = 0; st < S - 1; ++st) {
+      const int64_t q0 = (int64_t)blockIdx.x + (int64_t)st * gridDim.x;
+      if (q0 < nchunks) {
+        if (warp == 0) stage_w(q0, st);
+        stage_v(q0, st);
+      }
+      cp_async_commit();
     }
-    cp_async_commit();
   }
   unsigned iter = 0;
   for (int64_t q = blockIdx.x; q < nchunks; q += gridDim.x, buf ^= 1, ++iter) {
     const int64_t base = q * ROWS + lane;
     const bool full = q * ROWS + ROWS <= a.n;
-    const int64_t qn = q + gridDim.x;
+    const int slot = (int)(iter % S);
     cplx wv[R];
     cplx v[CT][R];
     if (PF) {
-      if (qn < nchunks) stage_v(qn, buf ^ 1);
+      // refill the slot consumed in the previous iteration (its readers are past barrier 2)
+      const int64_t qn = q + (int64_t)(S - 1) * gridDim.x;
+      const int nslot = (int)((iter + S - 1) % S);
+      if (qn < nchunks) {
+        if (warp == 0) stage_w(qn, nslot);
+        stage_v(qn, nslot);
+      }
       cp_async_commit();
-      cp_async_wait<1>();  // everything but the group just committed has landed
+      cp_async_wait<S - 1>();  // all but the S - 1 newest groups have landed: this chunk is in
       __syncwarp();
-      const cplx* src = sv + ((size_t)buf * nwarps + warp) * CT * ROWS;
+      const cplx* src = sv + ((size_t)slot * nwarps + warp) * CT * ROWS;
 #pragma unroll
       for (int k = 0; k < CT; ++k)
         if (k < mycols) {
@@ -491,7 +502,7 @@ __global__ void __launch_bounds__(CT < 5 ? 256 : 512) cgs_fused_kernel(OrthoArgs
     if (warp == (int)(iter % nwarps)) {
       if (PF) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) wv[r] = sw[(size_t)buf * ROWS + r * kWarp + lane];
+        for (int r = 0; r < R; ++r) wv[r] = sw[(size_t)slot * ROWS + r * kWarp + lane];
       }
       const cplx* all = spart + (size_t)buf * nwarps * ROWS;
 #pragma unroll
@@ -508,11 +519,6 @@ __global__ void __launch_bounds__(CT < 5 ? 256 : 512) cgs_fused_kernel(OrthoArgs
           nacc = fma(wv[r].y, wv[r].y, nacc);
         }
       }
-    }
-    if (PF) {
-      // every warp is past its reads of sw[buf ^ 1] (previous chunk): refill it
-      if (warp == 0 && qn < nchunks) stage_w(qn, buf ^ 1);
-      cp_async_commit();
     }
     __syncthreads();  // w' of the chunk is published
 #pragma unroll
@@ -766,31 +772,45 @@ static int resident_blocks(K kernel, int threads, size_t smem, int* cache) {
   return *cache;
 }
 
-template <int CT, int R, bool PF, bool REAL>
-static cudaError_t launch_fused_tr(const OrthoArgs& a, int warps, int num_sms, cudaStream_t st,
-                                   int grid_mult) {
+template <int CT, int R, bool PF, bool REAL, int S>
+static cudaError_t launch_fused_trs(const OrthoArgs& a, int warps, int num_sms, cudaStream_t st,
+                                    int grid_mult) {
   OrthoArgs args = a;
   args.accumulate = 1;  // the dots it produces belong to round 2
   const int threads = warps * kWarp;
   constexpr int ROWS = kWarp * R;
   const int64_t nchunks = (a.n + ROWS - 1) / ROWS;
   size_t smem = sizeof(cplx) * ((size_t)2 * warps * ROWS + (size_t)warps * CT + ROWS);
-  if (PF) smem += sizeof(cplx) * ((size_t)2 * ROWS + (size_t)2 * warps * CT * ROWS);
+  if (PF) smem += sizeof(cplx) * ((size_t)S * ROWS + (size_t)S * warps * CT * ROWS);
   const size_t need = sizeof(double) * (2 * a.ncols + 2);
   if (smem < need) smem = need;
   static int occ[17] = {0};
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(cgs_fused_kernel<CT, R, PF, REAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncSetAttribute(cgs_fused_kernel<CT, R, PF, REAL, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          200 * 1024);
     attr_done = true;
   }
   const int bps = grid_mult > 0 ? grid_mult
-                                : resident_blocks(cgs_fused_kernel<CT, R, PF, REAL>, threads, smem,
+                                : resident_blocks(cgs_fused_kernel<CT, R, PF, REAL, S>, threads, smem,
                                                   &occ[warps]);
   const int grid = pick_grid(nchunks, bps, num_sms, a.grid_cap);
-  cgs_fused_kernel<CT, R, PF, REAL><<<grid, threads, smem, st>>>(args);
+  cgs_fused_kernel<CT, R, PF, REAL, S><<<grid, threads, smem, st>>>(args);
   return cudaGetLastError();
+}
+template <int CT, int R, bool PF, bool REAL>
+static cudaError_t launch_fused_tr(const OrthoArgs& a, int warps, int num_sms, cudaStream_t st,
+                                   int grid_mult) {
+  // staging depth: as many chunks in flight as fit beside a second resident block (<= ~100 KB)
+  if (PF) {
+    const size_t per_stage = sizeof(cplx) * (size_t)kWarp * R * ((size_t)warps * CT + 1);
+    const int want = a.stages > 0 ? a.stages : (3 * per_stage <= 100 * 1024 ? 3 : 2);
+    if (want >= 4 && 4 * per_stage <= 200 * 1024)
+      return launch_fused_trs<CT, R, PF, REAL, 4>(a, warps, num_sms, st, grid_mult);
+    if (want == 3 && 3 * per_stage <= 200 * 1024)
+      return launch_fused_trs<CT, R, PF, REAL, 3>(a, warps, num_sms, st, grid_mult);
+  }
+  return launch_fused_trs<CT, R, PF, REAL, 2>(a, warps, num_sms, st, grid_mult);
 }
 template <int CT, int R, bool PF>
 static cudaError_t launch_fused_t(const OrthoArgs& a, int warps, int num_sms, cudaStream_t st,

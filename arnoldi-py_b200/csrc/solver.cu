@@ -123,7 +123,7 @@ struct ab200_solver {
 
   // options
   int opt_grid_mult = 0, opt_restart_variant = 0, opt_ortho_variant = 0, opt_spmv_tile = 0,
-      opt_fused_ct = 0, opt_spmv_threads = 0;
+      opt_fused_ct = 0, opt_spmv_threads = 0, opt_fused_stages = 0;
 
   // stats
   bool timing = false;
@@ -281,6 +281,7 @@ static OrthoArgs make_ortho_args(ab200_solver* s, cplx* w, int ncols, int j, dou
   a.accumulate = 0;
   a.finalize = finalize;
   a.grid_cap = s->grid_cap;
+  a.stages = s->opt_fused_stages;
   a.tol = tol;
   a.eta = eta;
   a.scale = s->scale;
@@ -1093,6 +1094,8 @@ int ab200_set_option(ab200_solver* s, const char* key, int64_t value) {
     s->opt_restart_variant = (int)value;
   else if (!strcmp(key, "ortho_variant"))
     s->opt_ortho_variant = (int)value;
+  else if (!strcmp(key, "fused_stages"))
+    s->opt_fused_stages = (int)value;
   else if (!strcmp(key, "fused_ct"))
     s->opt_fused_ct = (int)value;
   else if (!strcmp(key, "real_mode")) {
