@@ -20,6 +20,7 @@ struct OrthoArgs {
   int finalize;      // write H[j+1, j], scale[j+1], breakdown flag when the step ends
   int grid_cap;      // capacity (in blocks) of the partial buffers
   int stages;        // cp.async staging depth of the fused sweep (0 = automatic)
+  int fused_r;       // rows pairs per lane and chunk in the fused sweep (0 = automatic)
   double tol;        // breakdown threshold (absolute, ortho.py:107)
   double eta;        // DGKS factor (ortho.py:101)
   double* scale;     // [max_dim + 1]
@@ -59,6 +60,8 @@ struct SpmvArgs {
   int tile;                // nnz staged per block iteration
   int threads;             // block size: 128 or 256
   int long_rows;           // some row has more than 16 entries: warp-per-row path compiled in
+  int variant;             // 0 = streaming (cp.async, persistent) kernel when no long rows; 1 = plain
+  int num_sms;
   const StepCtl* ctl;      // nullptr for the stand-alone entry point
 };
 

@@ -804,7 +804,7 @@ static cudaError_t launch_fused_tr(const OrthoArgs& a, int warps, int num_sms, c
   // staging depth: as many chunks in flight as fit beside a second resident block (<= ~100 KB)
   if (PF) {
     const size_t per_stage = sizeof(cplx) * (size_t)kWarp * R * ((size_t)warps * CT + 1);
-    const int want = a.stages > 0 ? a.stages : (3 * per_stage <= 100 * 1024 ? 3 : 2);
+    const int want = a.stages > 0 ? a.stages : 2;  // measured: deeper rings cost a resident block
     if (want >= 4 && 4 * per_stage <= 200 * 1024)
       return launch_fused_trs<CT, R, PF, REAL, 4>(a, warps, num_sms, st, grid_mult);
     if (want == 3 && 3 * per_stage <= 200 * 1024)
@@ -840,6 +840,14 @@ cudaError_t launch_cgs_fused(const OrthoArgs& a, int num_sms, cudaStream_t st, i
   // still leave two blocks per SM
   const int rr = ct <= 5 ? 2 : 1;
   const size_t stage_bytes = (size_t)2 * warps * ct * rr * kWarp * sizeof(cplx);
+  if (variant != 2 && a.fused_r == 1) {  // A/B: one row pair per lane and chunk
+    switch (ct) {
+      case 3: return launch_fused_t<3, 1, true>(a, warps, num_sms, st, grid_mult);
+      case 4: return launch_fused_t<4, 1, true>(a, warps, num_sms, st, grid_mult);
+      case 5: return launch_fused_t<5, 1, true>(a, warps, num_sms, st, grid_mult);
+      default: break;
+    }
+  }
   if (variant != 2 && stage_bytes <= 96 * 1024) {
     switch (ct) {
       case 1: return launch_fused_t<1, 2, true>(a, warps, num_sms, st, grid_mult);

@@ -123,7 +123,7 @@ struct ab200_solver {
 
   // options
   int opt_grid_mult = 0, opt_restart_variant = 0, opt_ortho_variant = 0, opt_spmv_tile = 0,
-      opt_fused_ct = 0, opt_spmv_threads = 0, opt_fused_stages = 0;
+      opt_fused_ct = 0, opt_spmv_threads = 0, opt_fused_stages = 0, opt_fused_r = 0, opt_spmv_variant = 0;
 
   // stats
   bool timing = false;
@@ -282,6 +282,7 @@ static OrthoArgs make_ortho_args(ab200_solver* s, cplx* w, int ncols, int j, dou
   a.finalize = finalize;
   a.grid_cap = s->grid_cap;
   a.stages = s->opt_fused_stages;
+  a.fused_r = s->opt_fused_r;
   a.tol = tol;
   a.eta = eta;
   a.scale = s->scale;
@@ -623,6 +624,8 @@ static int enqueue_spmv(ab200_solver* s, const void* x, void* y, const double* x
   a.threads = s->spmv_threads;
   a.real = (in_expand && s->real_mode) ? 1 : 0;
   a.long_rows = s->max_row_len > 16 ? 1 : 0;
+  a.variant = s->opt_spmv_variant;
+  a.num_sms = s->num_sms;
   a.ctl = in_expand ? s->ctl : nullptr;
   const double sv = s->value_kind == AB200_F64 ? 8.0 : 16.0;
   const double eb = a.real ? 8.0 : 16.0;
@@ -1094,6 +1097,10 @@ int ab200_set_option(ab200_solver* s, const char* key, int64_t value) {
     s->opt_restart_variant = (int)value;
   else if (!strcmp(key, "ortho_variant"))
     s->opt_ortho_variant = (int)value;
+  else if (!strcmp(key, "spmv_variant"))
+    s->opt_spmv_variant = (int)value;
+  else if (!strcmp(key, "fused_r"))
+    s->opt_fused_r = (int)value;
   else if (!strcmp(key, "fused_stages"))
     s->opt_fused_stages = (int)value;
   else if (!strcmp(key, "fused_ct"))

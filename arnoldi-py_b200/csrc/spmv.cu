@@ -76,10 +76,13 @@ __global__ void spmv_maxrow_kernel(const IdxT* __restrict__ indptr, int64_t n, i
 template <typename IdxT>
 __global__ void spmv_plan_kernel(const IdxT* __restrict__ indptr, int64_t n, int64_t nnz, int tile,
                                  int nblocks, int64_t* __restrict__ rowblk) {
+  // rowblk[b] = first row of tile b; rowblk[nblocks + 1 + b] = indptr of that row
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b > nblocks) return;
+  int64_t* __restrict__ nnzblk = rowblk + nblocks + 1;
   if (b == nblocks) {
     rowblk[b] = n;
+    nnzblk[b] = nnz;
     return;
   }
   const int64_t target = (int64_t)b * tile;
@@ -93,6 +96,7 @@ __global__ void spmv_plan_kernel(const IdxT* __restrict__ indptr, int64_t n, int
       hi = mid;
   }
   rowblk[b] = lo;
+  nnzblk[b] = (int64_t)indptr[lo];
 }
 
 // LONG = false: the matrix has no row longer than kShortRow, the warp-per-row machinery is
@@ -211,6 +215,108 @@ __global__ void __launch_bounds__(kSpmvThreads) spmv_tile_kernel(SpmvArgs a) {
   }
 }
 
+// ------------------------------------------------------------------ streaming kernel
+// For matrices whose rows all have at most kShortRow entries (mark, the Laplacians).
+// Persistent blocks walk the tiles; the NEXT tile's values, column ids and row pointers are
+// staged with cp.async (LDGSTS: no register round trip) while the current tile's rows are
+// summed, so the four dependent memory round trips of the plain kernel (tile bounds -> row
+// pointers -> staging -> gathers) are taken off the critical path.  Same arithmetic, same
+// order: y is bit-identical to scipy's csr_matvec.
+__device__ __forceinline__ void cpa16(void* dst, const void* src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+}
+template <int BYTES>
+__device__ __forceinline__ void cpa_small(void* dst, const void* src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(src), "n"(BYTES) : "memory");
+}
+
+template <typename IdxT, typename ValT, typename XT, int THREADS>
+__global__ void __launch_bounds__(THREADS) spmv_stream_kernel(SpmvArgs a) {
+  if (a.ctl != nullptr && a.ctl->stop) return;
+  constexpr int RP = 2 * THREADS + 2;  // row pointers staged per tile (more rows: read from global)
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int cap = a.tile + kShortRow + 8;  // entries per stage (a tile overshoots by < one row)
+  const size_t stage_bytes =
+      ((size_t)cap * (sizeof(ValT) + sizeof(int32_t)) + (size_t)RP * sizeof(IdxT) + 15) / 16 * 16;
+  const IdxT* __restrict__ indptr = static_cast<const IdxT*>(a.indptr);
+  const ValT* __restrict__ values = static_cast<const ValT*>(a.values);
+  const int32_t* __restrict__ indices = a.indices;
+  const XT* __restrict__ x = static_cast<const XT*>(a.x);
+  const XT* __restrict__ ghost = static_cast<const XT*>(a.ghost);
+  XT* __restrict__ yout = static_cast<XT*>(a.y);
+  const int64_t* __restrict__ rowblk = a.rowblk;
+  const int64_t* __restrict__ nnzblk = a.rowblk + a.nblocks + 1;
+  const int64_t nloc = a.n_local_cols;
+  const double xs = a.xscale ? *a.xscale : 1.0;
+  const int tid = threadIdx.x;
+
+  auto stage = [&](int b, int st) {
+    unsigned char* base = smem_raw + (size_t)st * stage_bytes;
+    ValT* sval = reinterpret_cast<ValT*>(base);
+    int32_t* scol = reinterpret_cast<int32_t*>(base + (size_t)cap * sizeof(ValT));
+    IdxT* srow = reinterpret_cast<IdxT*>(base + (size_t)cap * (sizeof(ValT) + sizeof(int32_t)));
+    const int64_t r0 = rowblk[b], r1 = rowblk[b + 1];
+    const int64_t s = nnzblk[b], e = nnzblk[b + 1];
+    const int64_t ca = s & ~(int64_t)3;
+    const int tot = (int)(e - ca);
+    const int nvec = (tot + 3) >> 2;  // the arrays are padded by 4 entries: reading past e is safe
+    for (int k = tid; k < nvec; k += THREADS) cpa16(scol + 4 * k, indices + ca + 4 * k);
+    if (sizeof(ValT) == 8) {
+      for (int k = tid; k < 2 * nvec; k += THREADS) cpa16(sval + 2 * k, values + ca + 2 * k);
+    } else {
+      for (int k = tid; k < 4 * nvec; k += THREADS) cpa16(sval + k, values + ca + k);
+    }
+    int64_t nr = r1 - r0 + 1;
+    if (nr > RP) nr = RP;
+    for (int k = tid; k < (int)nr; k += THREADS) cpa_small<sizeof(IdxT)>(srow + k, indptr + r0 + k);
+  };
+
+  int b = blockIdx.x;
+  if (b < a.nblocks) stage(b, 0);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  int st = 0;
+  for (; b < a.nblocks; b += gridDim.x, st ^= 1) {
+    const int bn = b + gridDim.x;
+    if (bn < a.nblocks) stage(bn, st ^ 1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncthreads();  // this tile's stage is complete and visible to every thread
+    unsigned char* base = smem_raw + (size_t)st * stage_bytes;
+    const ValT* sval = reinterpret_cast<const ValT*>(base);
+    const int32_t* scol = reinterpret_cast<const int32_t*>(base + (size_t)cap * sizeof(ValT));
+    const IdxT* srow = reinterpret_cast<const IdxT*>(base + (size_t)cap * (sizeof(ValT) + sizeof(int32_t)));
+    const int64_t r0 = rowblk[b], r1 = rowblk[b + 1];
+    const int64_t ca = nnzblk[b] & ~(int64_t)3;
+    for (int64_t rl = tid; rl < r1 - r0; rl += THREADS) {
+      const int64_t rs = rl + 1 < RP ? (int64_t)srow[rl] : (int64_t)indptr[r0 + rl];
+      const int64_t re = rl + 1 < RP ? (int64_t)srow[rl + 1] : (int64_t)indptr[r0 + rl + 1];
+      XT acc = xzero<XT>();
+      int k = (int)(rs - ca);
+      const int kend = (int)(re - ca);
+      for (; k + 4 <= kend; k += 4) {
+        XT xv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int64_t col = scol[k + u];
+          xv[u] = (col < nloc) ? ld_ro(x + col) : ld_ro(ghost + (col - nloc));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc = cadd_rn(acc, vmul(sval[k + u], xv[u]));
+      }
+      for (; k < kend; ++k) {
+        const int64_t col = scol[k];
+        const XT xv = (col < nloc) ? ld_ro(x + col) : ld_ro(ghost + (col - nloc));
+        acc = cadd_rn(acc, vmul(sval[k], xv));
+      }
+      yout[r0 + rl] = cscale(acc, xs);
+    }
+    __syncthreads();  // everyone is done with this stage before it is refilled
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 cudaError_t launch_spmv_maxrow(const void* indptr, int indptr_bits, int64_t n, int* out,
                                cudaStream_t st) {
   int64_t grid = (n + 255) / 256;
@@ -251,7 +357,28 @@ static cudaError_t launch_spmv_ttl(const SpmvArgs& a, cudaStream_t st) {
   return cudaGetLastError();
 }
 template <typename IdxT, typename ValT, typename XT, int THREADS>
+static cudaError_t launch_spmv_stream(const SpmvArgs& a, cudaStream_t st) {
+  const int cap = a.tile + kShortRow + 8;
+  const size_t stage_bytes = ((size_t)cap * (sizeof(ValT) + sizeof(int32_t)) +
+                              (size_t)(2 * THREADS + 2) * sizeof(IdxT) + 15) / 16 * 16;
+  const size_t smem = 2 * stage_bytes;
+  static int occ = 0;
+  if (occ == 0) {
+    cudaFuncSetAttribute(spmv_stream_kernel<IdxT, ValT, XT, THREADS>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+            &occ, spmv_stream_kernel<IdxT, ValT, XT, THREADS>, THREADS, smem) != cudaSuccess ||
+        occ < 1)
+      occ = 1;
+  }
+  int64_t grid = (int64_t)a.num_sms * occ;
+  if (grid > a.nblocks) grid = a.nblocks;
+  spmv_stream_kernel<IdxT, ValT, XT, THREADS><<<(int)grid, THREADS, smem, st>>>(a);
+  return cudaGetLastError();
+}
+template <typename IdxT, typename ValT, typename XT, int THREADS>
 static cudaError_t launch_spmv_tt(const SpmvArgs& a, cudaStream_t st) {
+  if (!a.long_rows && a.variant != 1) return launch_spmv_stream<IdxT, ValT, XT, THREADS>(a, st);
   return a.long_rows ? launch_spmv_ttl<IdxT, ValT, XT, THREADS, true>(a, st)
                      : launch_spmv_ttl<IdxT, ValT, XT, THREADS, false>(a, st);
 }

@@ -69,7 +69,7 @@ def main():
     cycle()
     for spec in args.sets:
         opts = dict(kv.split("=") for kv in spec.split(",") if kv)
-        for k in ("ortho_variant", "fused_ct", "grid_mult", "restart_variant", "fused_stages"):
+        for k in ("ortho_variant", "fused_ct", "grid_mult", "restart_variant", "fused_stages", "fused_r", "spmv_variant"):
             dev.set_option(k, int(opts.get(k, 0)))
         if "spmv_tile" in opts or "spmv_threads" in opts:
             dev.set_option("spmv_tile", int(opts.get("spmv_tile", 0)))
