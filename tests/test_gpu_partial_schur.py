@@ -295,3 +295,53 @@ def test_real_storage_is_lossless(gpu, golden):
                                sort_function=arg_largest_real, stats=stats)
     _check_against_record(A, Q, T, hist, stats, g, "lap2d64_s0", 1e-8, restart_slack=4)
     assert stats["real_storage"] == 1
+
+
+def test_partial_schur_option_coverage(gpu):
+    """Arguments the reference accepts beyond the recorded solves: custom p, a user
+    sort_function (smallest real part), nev = 1, int64 CSR indices, max_dim = n."""
+    import scipy.sparse as sp
+    from arnoldi_b200 import partial_schur
+    from arnoldi_b200.matrices import mark
+    A = mark(12)                                   # n = 78
+    n = A.shape[0]
+    dense_eigs = np.linalg.eigvals(A.toarray())
+
+    def smallest_real(x):
+        return np.argsort(np.real(x))
+
+    for kw, want in (
+        (dict(nev=1, max_dim=12), np.sort(dense_eigs.real)[::-1][:1]),
+        (dict(nev=4, max_dim=30, p=6), np.sort(dense_eigs.real)[::-1][:4]),
+        (dict(nev=3, max_dim=25, sort_function=smallest_real), np.sort(dense_eigs.real)[:3]),
+    ):
+        kw = dict(kw)
+        sort = kw.pop("sort_function", None) or oracle.arg_largest_real
+        np.random.seed(5)
+        Q, T, hist = partial_schur(A, kw.pop("nev"), stopping_criterion=1e-9, max_restarts=3000,
+                                   sort_function=sort, **kw)
+        np.random.seed(5)
+        Qo, To, ho = oracle.partial_schur(A, T.shape[0], stopping_criterion=1e-9,
+                                          max_restarts=3000, sort_function=sort, **kw)
+        np.testing.assert_allclose(np.diag(T).real, want, atol=1e-7)
+        np.testing.assert_allclose(np.diag(T), np.diag(To), rtol=1e-8, atol=1e-10)
+        assert abs(int(hist.restarts[0]) - int(ho.restarts[0])) <= 2
+        assert np.linalg.norm(A @ Q - Q @ T, axis=0).max() < 1e-7
+    # int64 index arrays (what scipy switches to above 2^31 entries)
+    B = sp.csr_matrix((A.data, A.indices.astype(np.int64), A.indptr.astype(np.int64)), shape=A.shape)
+    np.random.seed(5)
+    Q1, T1, h1 = partial_schur(A, 3, max_dim=20, stopping_criterion=1e-9, max_restarts=2000,
+                               sort_function=oracle.arg_largest_real)
+    np.random.seed(5)
+    Q2, T2, h2 = partial_schur(B, 3, max_dim=20, stopping_criterion=1e-9, max_restarts=2000,
+                               sort_function=oracle.arg_largest_real)
+    np.testing.assert_array_equal(T1, T2)          # same arithmetic, bit for bit
+    np.testing.assert_array_equal(Q1, Q2)
+    # max_dim = n on a small symmetric operator: the Krylov space is the whole space
+    S = sp.diags_array([np.arange(1.0, 13.0), 0.1 * np.ones(11), 0.1 * np.ones(11)],
+                       offsets=[0, 1, -1]).tocsr()
+    np.random.seed(1)
+    Q, T, hist = partial_schur(S, 2, max_dim=11, stopping_criterion=1e-10, max_restarts=500,
+                               sort_function=oracle.arg_largest_real)
+    np.testing.assert_allclose(np.diag(T).real, np.sort(np.linalg.eigvalsh(S.toarray()))[::-1][:2],
+                               rtol=1e-9)
