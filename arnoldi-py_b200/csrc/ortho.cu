@@ -13,6 +13,8 @@
 // Every reduction is two-stage in a fixed order (lane butterfly -> per-block
 // partial -> last block sums the partials in block order), so results are
 // bit-reproducible run to run.  No floating-point atomics.
+#include <type_traits>
+
 #include "kernels.cuh"
 
 namespace ab200 {
@@ -583,6 +585,153 @@ __global__ void __launch_bounds__(CT < 5 ? 256 : 512) cgs_fused_kernel(OrthoArgs
   if (s_again) finish_dots(a, 0, c, red, false);
 }
 
+// ------------------------------------------------------------------ CGS fused pass, warp tiles
+// Same mathematics as cgs_fused_kernel (w' = w - U coef ; g' = U^H w' ; ||w'||^2 in one sweep),
+// different decomposition: every WARP owns a chunk of 32 elements x ALL c columns, staged into
+// a warp-private shared-memory tile with cp.async (double buffered).  The tile is read twice --
+// once to build w', once for the c dot products, whose accumulators live in registers -- so
+// no block barrier and no exchange of partial sums is needed in the sweep; warps only meet at
+// the very end.  Used for c <= 64 (tile size); wider bases use cgs_fused_kernel.
+template <int CMAX, bool REAL>
+__global__ void __launch_bounds__(256) cgs_fused_warp_kernel(OrthoArgs a) {
+  StepCtl* ctl = a.ctl;
+  if (ctl->stop) return;
+  extern __shared__ __align__(16) unsigned char fw_smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nwarps = blockDim.x >> 5;
+  const int c = a.ncols;
+  const int64_t ld = a.ld;
+  cplx* w = a.w;
+  const cplx* __restrict__ U = a.U;
+  // layout: coef[CMAX] | per warp: tile[2][c + 1][32]   (slot c of a tile holds the chunk of w)
+  cplx* scoef = reinterpret_cast<cplx*>(fw_smem);
+  cplx* tiles = scoef + CMAX + (size_t)warp * 2 * (c + 1) * kWarp;
+  for (int i = threadIdx.x; i < CMAX; i += blockDim.x)
+    scoef[i] = i < c ? a.coef[i] : make_double2(0.0, 0.0);
+  __syncthreads();
+
+  typedef typename std::conditional<REAL, double, cplx>::type AccT;
+  AccT acc[CMAX];
+#pragma unroll
+  for (int i = 0; i < CMAX; ++i) acc[i] = AccT();
+  double nacc = 0.0;
+
+  const int64_t nchunks = (a.n + kWarp - 1) / kWarp;
+  const int64_t stride = (int64_t)gridDim.x * nwarps;
+  auto stage = [&](int64_t q, int b) {
+    const int64_t row = q * kWarp + lane;
+    const bool ok = row < a.n;
+    cplx* dst = tiles + (size_t)b * (c + 1) * kWarp + lane;
+    const cplx* src = U + (ok ? row : 0);
+    for (int i = 0; i < c; ++i) cp_async16(dst + i * kWarp, src + (int64_t)i * ld, ok);
+    cp_async16(dst + c * kWarp, w + (ok ? row : 0), ok);
+  };
+  int64_t q = (int64_t)blockIdx.x * nwarps + warp;
+  if (q < nchunks) stage(q, 0);
+  cp_async_commit();
+  int buf = 0;
+  for (; q < nchunks; q += stride, buf ^= 1) {
+    if (q + stride < nchunks) stage(q + stride, buf ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncwarp();
+    const cplx* tile = tiles + (size_t)buf * (c + 1) * kWarp + lane;
+    cplx t = make_double2(0.0, 0.0), t2 = make_double2(0.0, 0.0);
+    int i = 0;
+    for (; i + 2 <= c; i += 2) {  // two chains: the sums are short dependent chains otherwise
+      addax<REAL>(t, tile[i * kWarp], scoef[i]);
+      addax<REAL>(t2, tile[(i + 1) * kWarp], scoef[i + 1]);
+    }
+    if (i < c) addax<REAL>(t, tile[i * kWarp], scoef[i]);
+    cplx wv = tile[c * kWarp];
+    wv.x -= (t.x + t2.x);
+    wv.y -= (t.y + t2.y);
+    const int64_t row = q * kWarp + lane;
+    if (row < a.n) {
+      st_stream(w + row, wv);
+      nacc = fma(wv.x, wv.x, nacc);
+      nacc = fma(wv.y, wv.y, nacc);
+    }
+#pragma unroll
+    for (int k = 0; k < CMAX; ++k) {
+      if (k < c) {
+        const cplx v = tile[k * kWarp];
+        if (REAL) {
+          double& ar = *reinterpret_cast<double*>(&acc[k]);
+          ar = fma(v.x, wv.x, ar);
+          ar = fma(v.y, wv.y, ar);
+        } else {
+          cfma_conj(*reinterpret_cast<cplx*>(&acc[k]), v, wv);
+        }
+      }
+    }
+    __syncwarp();  // the tile may be refilled by the next iteration's staging
+  }
+  cp_async_wait<0>();
+  __syncthreads();  // every warp is done with its tiles: the space is re-used below
+
+  // block-level combine: warp sums -> shared -> one partial per block and column
+  cplx* bp = reinterpret_cast<cplx*>(fw_smem) + CMAX;  // [nwarps][CMAX]
+#pragma unroll
+  for (int k = 0; k < CMAX; ++k) {
+    if (k < c) {
+      cplx v;
+      if (REAL) {
+        v = make_double2(warp_sum(*reinterpret_cast<double*>(&acc[k])), 0.0);
+      } else {
+        v = warp_sum(*reinterpret_cast<cplx*>(&acc[k]));
+      }
+      if (lane == 0) bp[warp * CMAX + k] = v;
+    }
+  }
+  __shared__ double s_nw[8];
+  {
+    const double sN = warp_sum(nacc);
+    if (lane == 0) s_nw[warp] = sN;
+  }
+  __syncthreads();
+  const int gcap = a.grid_cap;
+  for (int k = threadIdx.x; k < c; k += blockDim.x) {
+    cplx v = make_double2(0.0, 0.0);
+    for (int wi = 0; wi < nwarps; ++wi) v = cadd(v, bp[wi * CMAX + k]);
+    a.part[(size_t)k * gcap + blockIdx.x] = v;
+  }
+  if (threadIdx.x == 0) {
+    double tN = 0.0;
+    for (int wi = 0; wi < nwarps; ++wi) tN += s_nw[wi];
+    a.npart[blockIdx.x] = tN;
+  }
+
+  __shared__ int s_last;
+  __shared__ int s_again;
+  if (!last_block_ticket(a.ticket, gridDim.x, &s_last)) return;
+
+  double* red = reinterpret_cast<double*>(fw_smem);  // 2*c + 1 doubles
+  for (int k = warp; k < c; k += nwarps) {
+    cplx g = sum_partials(a.part + (size_t)k * gcap, gridDim.x, lane);
+    if (lane == 0) {
+      red[2 * k] = g.x;
+      red[2 * k + 1] = g.y;
+    }
+  }
+  if (warp == 0) {
+    double sN = sum_partials(a.npart, gridDim.x, lane);
+    if (lane == 0) red[2 * c] = sN;
+  }
+  __syncthreads();
+  peer_allreduce(a.comm, red, 2 * c + 1, ctl);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double beta = sqrt(red[2 * c]);
+    const bool again = dgks_decide(a, beta);
+    if (!again) finalize_step(a, beta);
+    s_again = again ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_again) finish_dots(a, 0, c, red, false);
+}
+
 // ------------------------------------------------------------------ MGS step kernel
 // Kernel i of an MGS sweep (ortho.py:39-41 / :47-50), i = 0..c:
 //   if i > 0:  w -= coef[i-1] * U_{i-1}          (axpy of the previous column)
@@ -819,10 +968,49 @@ static cudaError_t launch_fused_t(const OrthoArgs& a, int warps, int num_sms, cu
                 : launch_fused_tr<CT, R, PF, false>(a, warps, num_sms, st, grid_mult);
 }
 
+template <int CMAX, bool REAL>
+static cudaError_t launch_fused_warp_t(const OrthoArgs& a, int num_sms, cudaStream_t st,
+                                       int grid_mult) {
+  OrthoArgs args = a;
+  args.accumulate = 1;
+  const size_t per_warp = sizeof(cplx) * (size_t)2 * (a.ncols + 1) * kWarp;
+  int warps = (int)((190 * 1024 - sizeof(cplx) * CMAX) / per_warp);
+  if (warps > 8) warps = 8;
+  if (warps < 1) return cudaErrorInvalidValue;
+  size_t smem = sizeof(cplx) * CMAX + per_warp * warps;
+  const size_t need = sizeof(cplx) * CMAX * (warps + 1) + sizeof(double) * (2 * a.ncols + 2);
+  if (smem < need) smem = need;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(cgs_fused_warp_kernel<CMAX, REAL>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_done = true;
+  }
+  const int64_t nchunks = (a.n + kWarp - 1) / kWarp;
+  const int64_t nb = (nchunks + warps - 1) / warps;
+  const int grid = pick_grid(nb, grid_mult > 0 ? grid_mult : 1, num_sms, a.grid_cap);
+  cgs_fused_warp_kernel<CMAX, REAL><<<grid, warps * kWarp, smem, st>>>(args);
+  return cudaGetLastError();
+}
+template <int CMAX>
+static cudaError_t launch_fused_warp(const OrthoArgs& a, int num_sms, cudaStream_t st, int gm) {
+  return a.real ? launch_fused_warp_t<CMAX, true>(a, num_sms, st, gm)
+                : launch_fused_warp_t<CMAX, false>(a, num_sms, st, gm);
+}
+
 // variant 0: cp.async-staged (prefetching) kernel; variant 2: register loads only.
 // fused_ct > 0 forces the column-tile width (when the block shape allows it).
 cudaError_t launch_cgs_fused(const OrthoArgs& a, int num_sms, cudaStream_t st, int grid_mult,
                              int variant, int fused_ct) {
+  if (variant == 4 && a.ncols <= 64) {  // warp-tile kernel
+    const int c = a.ncols;
+    if (c <= 16) return launch_fused_warp<16>(a, num_sms, st, grid_mult);
+    if (c <= 24) return launch_fused_warp<24>(a, num_sms, st, grid_mult);
+    if (c <= 32) return launch_fused_warp<32>(a, num_sms, st, grid_mult);
+    if (c <= 40) return launch_fused_warp<40>(a, num_sms, st, grid_mult);
+    if (c <= 48) return launch_fused_warp<48>(a, num_sms, st, grid_mult);
+    return launch_fused_warp<64>(a, num_sms, st, grid_mult);
+  }
   int ct, warps;
   pass1_shape(a.ncols, &ct, &warps);
   if (a.ncols >= 20) {
