@@ -176,12 +176,16 @@ int ab200_timer_stop(ab200_solver *s, double *elapsed_ms);
 /* Select kernel variants (for A/B measurements); value 0 = automatic.
  *   "ortho_variant"   CGS2 schedule: 0 = adaptive (fused sweep while the DGKS test fires on
  *                     most steps, two-sweep rounds otherwise), 1 = always two-sweep rounds,
- *                     2 = always fused (register loads), 3 = always fused (cp.async staging)
+ *                     2 = always fused (register loads), 3 = always fused (cp.async staging),
+ *                     4 = always fused, warp-private tiles (c <= 64)
  *   "fused_ct"        column-tile width of the fused sweep (1..8)
+ *   "fused_stages"    cp.async ring depth of the fused sweep (2..4)
+ *   "fused_r"         1 = one 16-byte element per lane and chunk in the fused sweep
  *   "restart_variant" outputs per warp of the restart kernel (4, 8, 16)
  *   "real_mode"       0 = keep the basis as complex128 from the start (default: float64
  *                     storage while A, v0 and every Q applied are real -- see DESIGN.md)
  *   "grid_mult"       resident blocks per SM for the orthogonalisation kernels
+ *   "spmv_variant"    1 = plain tile kernel even when every row is short (default: streaming)
  *   "spmv_tile"       non-zeros staged per SpMV block    } take effect at the next
  *   "spmv_threads"    SpMV block size, 128 or 256        } ab200_set_csr */
 int ab200_set_option(ab200_solver *s, const char *key, int64_t value);
