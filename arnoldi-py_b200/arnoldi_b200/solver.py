@@ -76,24 +76,25 @@ class DeviceSolver:
         _lib.check(self.lib.ab200_set_columns(self._h, int(col0), int(cols.shape[1]), _ptr(cols),
                                               int(cols.shape[0])))
 
-    def _pinned_array(self, ncols):
-        """(n, ncols) complex128 column-major array in page-locked host memory, freed when the
-        last view of it is garbage collected.  A device-to-host copy into it runs at PCIe speed,
-        against ~4 GB/s into freshly allocated pageable memory (one page fault per 4 KiB)."""
-        import weakref
-        nbytes = 16 * self.n * ncols
-        ptr = C.c_void_p()
-        if self.lib.ab200_host_alloc(C.byref(ptr), nbytes) != _lib.OK:
-            return None
-        buf = (C.c_char * nbytes).from_address(ptr.value)
-        weakref.finalize(buf, self.lib.ab200_host_free, ptr)
-        return np.frombuffer(buf, dtype=np.complex128).reshape((self.n, ncols), order="F")
+    @staticmethod
+    def _hugepage_hint(arr):
+        """Ask for transparent huge pages on a freshly allocated result array: the device-to-
+        host copy of a multi-GB Q is otherwise dominated by one page fault per 4 KiB."""
+        try:
+            libc = C.CDLL(None, use_errno=True)
+            addr = arr.ctypes.data
+            start = (addr + 0x1FFFFF) & ~0x1FFFFF
+            length = (addr + arr.nbytes - start) & ~0x1FFFFF
+            if length > 0:
+                libc.madvise(C.c_void_p(start), C.c_size_t(length), 14)   # MADV_HUGEPAGE
+        except Exception:
+            pass
 
     def get_columns(self, col0, ncols, out=None, pinned=False):
-        if out is None and pinned and self.n * ncols >= (1 << 22):
-            out = self._pinned_array(ncols)
         if out is None:
             out = np.empty((self.n, ncols), np.complex128, order="F")
+            if pinned and out.nbytes >= (64 << 20):
+                self._hugepage_hint(out)
         assert out.flags.f_contiguous and out.shape == (self.n, ncols)
         _lib.check(self.lib.ab200_get_columns(self._h, int(col0), int(ncols), _ptr(out), self.n))
         return out
