@@ -67,8 +67,8 @@ def main():
                 N = int(tag[5:7])
                 c = 2 - 2 * np.cos(np.arange(1, N + 1) * np.pi / (N + 1))
                 exact = (c[:, None] + c[None, :]).ravel()
-                dist = np.array([np.abs(exact - x).min() for x in lam.real])
-                assert dist.max() < 1e-7 and np.abs(lam.imag).max() < 1e-9, (tag, dist)
+                gap = np.array([np.abs(exact - x).min() for x in lam.real])
+                assert gap.max() < 1e-7 and np.abs(lam.imag).max() < 1e-9, (tag, gap)
             else:
                 assert R == Rref, (tag, R, Rref)
                 assert np.sum(rel > 1e-10) <= max(1, len(lam) // 10) and rel.max() < 1e-8, (tag, rel)
