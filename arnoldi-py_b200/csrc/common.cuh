@@ -142,4 +142,19 @@ __device__ __forceinline__ bool last_block_ticket(unsigned* ticket, unsigned nbl
   return *smem_flag != 0;
 }
 
+// Function attributes (opt-in shared memory) are per device: remember per device ordinal
+// whether a launcher has configured its kernel yet.
+constexpr int kMaxDevices = 64;
+struct PerDeviceOnce {
+  bool done[kMaxDevices] = {false};
+  bool first_use() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= kMaxDevices) return true;
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+  }
+};
+
 }  // namespace ab200

@@ -934,11 +934,10 @@ static cudaError_t launch_fused_trs(const OrthoArgs& a, int warps, int num_sms, 
   const size_t need = sizeof(double) * (2 * a.ncols + 2);
   if (smem < need) smem = need;
   static int occ[17] = {0};
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce once;
+  if (once.first_use()) {
     cudaFuncSetAttribute(cgs_fused_kernel<CT, R, PF, REAL, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          200 * 1024);
-    attr_done = true;
   }
   const int bps = grid_mult > 0 ? grid_mult
                                 : resident_blocks(cgs_fused_kernel<CT, R, PF, REAL, S>, threads, smem,
@@ -980,11 +979,10 @@ static cudaError_t launch_fused_warp_t(const OrthoArgs& a, int num_sms, cudaStre
   size_t smem = sizeof(cplx) * CMAX + per_warp * warps;
   const size_t need = sizeof(cplx) * CMAX * (warps + 1) + sizeof(double) * (2 * a.ncols + 2);
   if (smem < need) smem = need;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce once;
+  if (once.first_use()) {
     cudaFuncSetAttribute(cgs_fused_warp_kernel<CMAX, REAL>,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_done = true;
   }
   const int64_t nchunks = (a.n + kWarp - 1) / kWarp;
   const int64_t nb = (nchunks + warps - 1) / warps;

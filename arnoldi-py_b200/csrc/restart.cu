@@ -90,13 +90,12 @@ static cudaError_t launch_restart_t(const RestartArgs& a, int num_sms, cudaStrea
   size_t smem = sizeof(cplx) * (size_t)a.m * a.p;
   const bool qs = smem <= 100 * 1024;  // stage the coefficients in shared memory
   if (!qs) smem = 0;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce once;
+  if (once.first_use()) {
     cudaFuncSetAttribute(restart_kernel<PT, true, true>,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(restart_kernel<PT, true, false>,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    attr_done = true;
   }
   const int64_t nchunks = (a.n + kWarp - 1) / kWarp;
   int bps = 2048 / threads;

@@ -346,11 +346,10 @@ template <typename IdxT, typename ValT, typename XT, int THREADS, bool LONG>
 static cudaError_t launch_spmv_ttl(const SpmvArgs& a, cudaStream_t st) {
   const size_t smem = (size_t)(a.tile + 4) * (sizeof(ValT) + sizeof(int32_t)) + 16 +
                       sizeof(int64_t) * (size_t)(a.tile / 16 + 2);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce once;
+  if (once.first_use()) {
     cudaFuncSetAttribute(spmv_tile_kernel<IdxT, ValT, XT, THREADS, LONG>,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    attr_done = true;
   }
   const int grid = a.nblocks;  // one tile per block; blocks are small and many per SM
   spmv_tile_kernel<IdxT, ValT, XT, THREADS, LONG><<<grid, THREADS, smem, st>>>(a);
@@ -363,7 +362,8 @@ static cudaError_t launch_spmv_stream(const SpmvArgs& a, cudaStream_t st) {
                               (size_t)(2 * THREADS + 2) * sizeof(IdxT) + 15) / 16 * 16;
   const size_t smem = 2 * stage_bytes;
   static int occ = 0;
-  if (occ == 0) {
+  static PerDeviceOnce once;
+  if (once.first_use()) {
     cudaFuncSetAttribute(spmv_stream_kernel<IdxT, ValT, XT, THREADS>,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(
