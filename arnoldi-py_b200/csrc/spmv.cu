@@ -111,10 +111,6 @@ __global__ void __launch_bounds__(kSpmvThreads) spmv_tile_kernel(SpmvArgs a) {
   __shared__ int s_nlong;
   int64_t* s_long_row = reinterpret_cast<int64_t*>(
       smem_raw + (size_t)(a.tile + 4) * (sizeof(ValT) + sizeof(int32_t)) + 8);  // [tile / 16 + 1]
-  // LONG: products val * x[col] of the whole tile (one round of independent gathers with
-  // many in flight per thread; the row sums then only read shared memory)
-  XT* sprod = reinterpret_cast<XT*>(smem_raw + (size_t)(a.tile + 4) * (sizeof(ValT) + sizeof(int32_t)) +
-                                    16 + sizeof(int64_t) * (size_t)(a.tile / 16 + 2));
 
   const IdxT* __restrict__ indptr = static_cast<const IdxT*>(a.indptr);
   const ValT* __restrict__ values = static_cast<const ValT*>(a.values);
@@ -158,27 +154,6 @@ __global__ void __launch_bounds__(kSpmvThreads) spmv_tile_kernel(SpmvArgs a) {
         }
       }
       __syncthreads();
-      if (LONG) {
-        // ---- products: thread k takes entries k, k + T, ...; four gathers in flight at a time
-        int k = tid;
-        for (; k + 3 * kSpmvThreads < tot; k += 4 * kSpmvThreads) {
-          XT xv[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int64_t col = scol[k + u * kSpmvThreads];
-            xv[u] = (col < nloc) ? ld_ro(x + col) : ld_ro(ghost + (col - nloc));
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-            sprod[k + u * kSpmvThreads] = vmul(sval[k + u * kSpmvThreads], xv[u]);
-        }
-        for (; k < tot; k += kSpmvThreads) {
-          const int64_t col = scol[k];
-          const XT xv = (col < nloc) ? ld_ro(x + col) : ld_ro(ghost + (col - nloc));
-          sprod[k] = vmul(sval[k], xv);
-        }
-        __syncthreads();
-      }
       // ---- one thread per row, stored order
       for (int64_t row = r0 + tid; row < r1; row += kSpmvThreads) {
         const int64_t rs = (int64_t)indptr[row], re = (int64_t)indptr[row + 1];
@@ -195,9 +170,6 @@ __global__ void __launch_bounds__(kSpmvThreads) spmv_tile_kernel(SpmvArgs a) {
         XT acc = (rs < cs) ? yout[row] : xzero<XT>();
         int k = (int)(lo - ca);
         const int kend = (int)(hi - ca);
-        if (LONG) {
-          for (; k < kend; ++k) acc = cadd_rn(acc, sprod[k]);  // same products, same order
-        }
 
         for (; k + 4 <= kend; k += 4) {
           XT xv[4];
@@ -227,8 +199,11 @@ __global__ void __launch_bounds__(kSpmvThreads) spmv_tile_kernel(SpmvArgs a) {
         const int64_t lo = rs > cs ? rs : cs;
         const int64_t hi = re < ce ? re : ce;
         XT acc = xzero<XT>();
-        for (int k = (int)(lo - ca) + (tid & 31); k < (int)(hi - ca); k += kWarp)
-          acc = cadd_rn(acc, sprod[k]);
+        for (int k = (int)(lo - ca) + (tid & 31); k < (int)(hi - ca); k += kWarp) {
+          const int64_t col = scol[k];
+          const XT xv = (col < nloc) ? ld_ro(x + col) : ld_ro(ghost + (col - nloc));
+          acc = cadd_rn(acc, vmul(sval[k], xv));
+        }
         acc = warp_sum(acc);
         if ((tid & 31) == 0) {
           XT t = (rs < cs) ? cadd_rn(yout[row], acc) : acc;
@@ -369,9 +344,8 @@ cudaError_t launch_spmv_plan(const void* indptr, int indptr_bits, int64_t n, int
 
 template <typename IdxT, typename ValT, typename XT, int THREADS, bool LONG>
 static cudaError_t launch_spmv_ttl(const SpmvArgs& a, cudaStream_t st) {
-  size_t smem = (size_t)(a.tile + 4) * (sizeof(ValT) + sizeof(int32_t)) + 16 +
-                sizeof(int64_t) * (size_t)(a.tile / 16 + 2);
-  if (LONG) smem += sizeof(XT) * (size_t)(a.tile + 4);
+  const size_t smem = (size_t)(a.tile + 4) * (sizeof(ValT) + sizeof(int32_t)) + 16 +
+                      sizeof(int64_t) * (size_t)(a.tile / 16 + 2);
   static PerDeviceOnce once;
   if (once.first_use()) {
     cudaFuncSetAttribute(spmv_tile_kernel<IdxT, ValT, XT, THREADS, LONG>,
