@@ -119,14 +119,33 @@ static cudaError_t launch_restart_t(const RestartArgs& a, int num_sms, cudaStrea
 }
 
 cudaError_t launch_restart(const RestartArgs& a, int num_sms, cudaStream_t st, int variant) {
-  // PT outputs per warp; at most 16 warps per block
-  // default: the fewest warps per row group (p <= 16 needs no block barrier at all)
-  int pt = variant > 0 ? variant : (a.p <= 8 ? 8 : 16);
+  // Outputs per warp: the fewest warps per row group (p <= 16 needs no block barrier at all),
+  // and the p outputs spread evenly over them (p = 25 -> 13 + 12, not 16 + 9: the block is as
+  // slow as its busiest warp and this kernel is FP64-bound)
+  int pt;
+  if (variant > 0) {
+    pt = variant;
+  } else {
+    const int nw = (a.p + 15) / 16;
+    pt = (a.p + nw - 1) / nw;
+    if (pt < 8) pt = 8;
+  }
   while ((a.p + pt - 1) / pt > 16) pt *= 2;
-  if (pt <= 4) return launch_restart_t<4>(a, num_sms, st);
-  if (pt <= 8) return launch_restart_t<8>(a, num_sms, st);
-  if (pt <= 16) return launch_restart_t<16>(a, num_sms, st);
-  return cudaErrorInvalidValue;
+  switch (pt) {
+    case 4: return launch_restart_t<4>(a, num_sms, st);
+    case 8: return launch_restart_t<8>(a, num_sms, st);
+    case 9: return launch_restart_t<9>(a, num_sms, st);
+    case 10: return launch_restart_t<10>(a, num_sms, st);
+    case 11: return launch_restart_t<11>(a, num_sms, st);
+    case 12: return launch_restart_t<12>(a, num_sms, st);
+    case 13: return launch_restart_t<13>(a, num_sms, st);
+    case 14: return launch_restart_t<14>(a, num_sms, st);
+    case 15: return launch_restart_t<15>(a, num_sms, st);
+    case 16: return launch_restart_t<16>(a, num_sms, st);
+    default: break;
+  }
+  if (pt < 8) return launch_restart_t<8>(a, num_sms, st);
+  return launch_restart_t<16>(a, num_sms, st);
 }
 
 // ------------------------------------------------------------------ materialise scales
