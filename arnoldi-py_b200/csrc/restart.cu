@@ -128,7 +128,7 @@ cudaError_t launch_restart(const RestartArgs& a, int num_sms, cudaStream_t st, i
   } else {
     const int nw = (a.p + 15) / 16;
     pt = (a.p + nw - 1) / nw;
-    if (pt < 8) pt = 8;
+    if (nw == 1) pt = a.p <= 8 ? 8 : 16;  // single warp: the full-width variants measured faster
   }
   while ((a.p + pt - 1) / pt > 16) pt *= 2;
   switch (pt) {
