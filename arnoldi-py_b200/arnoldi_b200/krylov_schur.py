@@ -156,8 +156,9 @@ def partial_schur(
                 raise ValueError("Happy breakdown not supported yet")
             reported = restart * (max_dim - nev) + (m - nev)  # krylov_schur.py:63
 
-            # rotate: the reference factors H_m, then re-factors the triangular result
-            # inside ordered_schur; both zgees calls are kept so Q matches to rounding
+            # rotate: zgees on H_m, then the reference's ordered_schur on the triangular result
+            # (its second zgees is an exact no-op on triangular input and is skipped, its
+            # ztrexc sequence is kept call for call so Q matches to rounding)
             T1, Q1 = schur(H[:m, :m], output="complex")
             T2, Q2 = ordered_schur(T1, output="complex", sort_function=sort_function)
             Q = Q1 @ Q2
@@ -192,7 +193,7 @@ def partial_schur(
         if not converged and raise_on_no_convergence:
             raise ValueError("Has not converged !")
         lap("host_schur")
-        Qout = dev.get_columns(0, nev, pinned=True)
+        Qout = dev.get_columns(0, nev, hugepages=True)
         lap("download_q")
         if multi:
             comm.barrier()   # nobody unmaps while a peer may still be in its last kernel

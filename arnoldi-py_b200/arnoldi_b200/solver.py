@@ -90,10 +90,10 @@ class DeviceSolver:
         except Exception:
             pass
 
-    def get_columns(self, col0, ncols, out=None, pinned=False):
+    def get_columns(self, col0, ncols, out=None, hugepages=False):
         if out is None:
             out = np.empty((self.n, ncols), np.complex128, order="F")
-            if pinned and out.nbytes >= (64 << 20):
+            if hugepages and out.nbytes >= (64 << 20):
                 self._hugepage_hint(out)
         assert out.flags.f_contiguous and out.shape == (self.n, ncols)
         _lib.check(self.lib.ab200_get_columns(self._h, int(col0), int(ncols), _ptr(out), self.n))

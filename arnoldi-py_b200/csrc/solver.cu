@@ -1055,6 +1055,11 @@ int ab200_reset_stats(ab200_solver* s) {
 
 int ab200_get_stats(ab200_solver* s, ab200_stats* out) {
   REQUIRE(s != nullptr && out != nullptr, "null argument");
+  if (!s->pending.empty()) {  // e.g. a restart update enqueued after the last expansion
+    CU(cudaSetDevice(s->device));
+    CU(cudaStreamSynchronize(s->stream));
+    resolve_pending(s, s->h_step_round2);
+  }
   *out = s->st;
   out->real_storage = s->real_mode ? 1 : 0;
   return AB200_OK;
