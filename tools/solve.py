@@ -4,7 +4,7 @@ time-to-k-converged, restart / matvec counts, true residuals and per-kernel figu
 
     python tools/solve.py --matrix lap2d --grid 4096 --nev 10 --max-dim 40
     python tools/solve.py --matrix mark --grid 4000 --nev 20 --max-dim 60
-    python tools/solve.py --matrix lap2d --grid 256 --nev 10 --max-dim 40 --oracle   # CPU beside it
+    (tests/solve_vs_oracle.py runs the same solve with the CPU oracle beside it)
 """
 import argparse
 import json
@@ -29,7 +29,6 @@ def main():
     ap.add_argument("--max-restarts", type=int, default=100000)
     ap.add_argument("--ortho", default="cgs2")
     ap.add_argument("--seed", type=int, default=0)
-    ap.add_argument("--oracle", action="store_true", help="also run the CPU oracle and compare")
     args = ap.parse_args()
 
     from arnoldi_b200 import matrices, partial_schur
@@ -61,22 +60,6 @@ def main():
                     for k in ("spmv", "ortho_pass1", "ortho_fused", "ortho_pass2", "mgs", "restart")
                     if stats[k + "_launches"]},
     }
-    if args.oracle:
-        import oracle
-        np.random.seed(args.seed)
-        cnt = {}
-        t0 = time.perf_counter()
-        Qo, To, ho = oracle.partial_schur(A, args.nev, max_dim=args.max_dim,
-                                          stopping_criterion=args.tol,
-                                          max_restarts=args.max_restarts,
-                                          sort_function=oracle.arg_largest_real,
-                                          ortho=oracle.cgs_dgks if args.ortho == "cgs2" else oracle.mgs_dgks,
-                                          counters=cnt)
-        dto = time.perf_counter() - t0
-        rel = np.abs(np.diag(T) - np.diag(To)) / np.abs(np.diag(To))
-        out["oracle"] = {"time_s": dto, "restarts": int(ho.restarts[0]),
-                         "true_matvecs": cnt["matvecs"], "max_rel_ritz_diff": float(rel.max()),
-                         "rel_ritz_diff": rel.tolist(), "cpu_count": os.cpu_count()}
     print(json.dumps(out), flush=True)
 
 
