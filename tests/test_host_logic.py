@@ -172,3 +172,23 @@ def test_ordered_schur_triangular_shortcut_is_exact():
             T2, Z2 = ordered_schur(T1, output="complex", sort_function=sort)
             np.testing.assert_array_equal(T2, T)
             np.testing.assert_array_equal(Z2, Z)
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the CPU arm the driver times beside the GPU arm) must run
+    without a GPU and print exactly one JSON line with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True,
+                         timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    rec = json.loads(lines[0])
+    assert rec["impl"] == "reference" and rec["unit"] == "matvec/s" and rec["value"] > 0
+    assert rec["higher_is_better"] is True and rec["vs_baseline"] is None
+    assert rec["cpu_baseline"]["kind"] == "port" and rec["cpu_baseline"]["cores"] >= 1
+    assert rec["e2e"]["h2d_bytes_per_step"] == 0 and rec["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in rec["config"]
