@@ -192,3 +192,22 @@ def test_bench_reference_arm_prints_one_json_line():
     assert rec["cpu_baseline"]["kind"] == "port" and rec["cpu_baseline"]["cores"] >= 1
     assert rec["e2e"]["h2d_bytes_per_step"] == 0 and rec["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in rec["config"]
+
+
+def test_reference_import_names_resolve_to_the_device_path():
+    """User code written against the reference (README.md:20-31) imports `arnoldi`; with this
+    repo's package directory on sys.path those names are the B200 implementations."""
+    import arnoldi
+    import arnoldi.krylov_schur
+    import arnoldi_b200
+    from arnoldi.decomposition import arnoldi_decomposition
+    from arnoldi.explicit_restarts import History
+    from arnoldi.matrices import mark
+    from arnoldi.ortho import dgks_gs, dgks_mgs
+    from arnoldi.utils import arg_largest_real, ordered_schur
+    assert arnoldi.partial_schur is arnoldi_b200.partial_schur
+    assert arnoldi.krylov_schur.partial_schur is arnoldi_b200.partial_schur
+    assert History is arnoldi_b200.History and mark(3).shape == (6, 6)
+    assert all(callable(f) for f in (arnoldi_decomposition, dgks_gs, dgks_mgs, arg_largest_real,
+                                     ordered_schur))
+    assert "arnoldi-py_b200" in arnoldi.__file__
