@@ -96,6 +96,25 @@ def build_halo_plan(block: RowBlock) -> HaloPlan:
     return HaloPlan(np.asarray(block.indptr), renum, np.asarray(block.data), ghost, r0, nloc)
 
 
+def plan_halo_push(ghost_lists, partition: RowPartition, rank: int):
+    """Owner-side view of the halo: given every rank's sorted ghost list, work out which LOCAL
+    rows of ``rank`` each peer reads and where they land in that peer's ghost buffer.
+
+    Returns ``(send_idx, send_ptr, dst_off)``: rows ``send_idx[send_ptr[r]:send_ptr[r+1]]`` (local
+    numbering, ascending) go to rank r, starting at index ``dst_off[r]`` of r's ghost buffer.
+    """
+    r0, r1 = partition.rows(rank)
+    send, ptr, dst = [], [0], []
+    for r, g in enumerate(ghost_lists):
+        g = np.asarray(g, dtype=np.int64)
+        lo, hi = (0, 0) if r == rank else (int(x) for x in np.searchsorted(g, [r0, r1]))
+        send.append(g[lo:hi] - r0)
+        ptr.append(ptr[-1] + (hi - lo))
+        dst.append(lo)
+    send_idx = np.ascontiguousarray(np.concatenate(send), dtype=np.int64)
+    return send_idx, np.array(ptr, dtype=np.int64), np.array(dst, dtype=np.int64)
+
+
 class TorchComm:
     """Bootstrap over torch.distributed (NCCL on the GPU box, gloo in CPU tests): only
     small host objects travel through it (IPC handles, barriers, max of timings)."""

@@ -154,18 +154,10 @@ class DeviceSolver:
         blob = C.create_string_buffer(256)
         _lib.check(self.lib.ab200_halo_export(self._h, blob))
         blobs = b"".join(comm.all_gather_bytes(blob.raw))
+        from .distributed import plan_halo_push
         lists = comm.all_gather_bytes(np.ascontiguousarray(ghost_cols, dtype=np.int64).tobytes())
-        r0, r1 = partition.rows(comm.rank)
-        send, ptr, dst = [], [0], []
-        for r in range(comm.world):
-            g = np.frombuffer(lists[r], dtype=np.int64)
-            lo, hi = (0, 0) if r == comm.rank else np.searchsorted(g, [r0, r1])
-            send.append(g[lo:hi] - r0)
-            ptr.append(ptr[-1] + int(hi - lo))
-            dst.append(int(lo))
-        send_idx = np.ascontiguousarray(np.concatenate(send), dtype=np.int64)
-        send_ptr = np.array(ptr, dtype=np.int64)
-        dst_off = np.array(dst, dtype=np.int64)
+        send_idx, send_ptr, dst_off = plan_halo_push(
+            [np.frombuffer(b, dtype=np.int64) for b in lists], partition, comm.rank)
         if send_idx.shape[0] == 0:
             send_idx = np.zeros(1, np.int64)
         _lib.check(self.lib.ab200_halo_connect(self._h, blobs, _ptr(send_idx), _ptr(send_ptr),

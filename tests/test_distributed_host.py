@@ -123,3 +123,29 @@ def test_world_size_2_gloo():
     assert sorted(o[0] for o in out) == [0, 1]
     assert all(o[1] and o[2] for o in out)
     assert all(o[3] == 1.0 for o in out)
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_halo_push_plan_is_the_transpose_of_the_pull_plan(world):
+    """Owner-side push lists: what rank q sends to rank r must be exactly the entries of r's
+    ghost list that q owns, in r's order, landing at the right offset of r's ghost buffer."""
+    from arnoldi_b200.distributed import (RowPartition, build_halo_plan, plan_halo_push,
+                                          slice_rows)
+    from arnoldi_b200.matrices import lap2d, powerlaw
+    for A in (lap2d(19), powerlaw(3000)):
+        n = A.shape[0]
+        part = RowPartition(n, world)
+        ghosts = [build_halo_plan(slice_rows(A, *part.rows(r))).ghost_cols for r in range(world)]
+        rng = np.random.default_rng(0)
+        x = rng.standard_normal(n)
+        received = [np.full(len(g), np.nan) for g in ghosts]
+        for q in range(world):
+            q0, q1 = part.rows(q)
+            send_idx, send_ptr, dst_off = plan_halo_push(ghosts, part, q)
+            assert send_ptr[0] == 0 and send_ptr[q + 1] == send_ptr[q]      # nothing to itself
+            for r in range(world):
+                rows = send_idx[send_ptr[r]:send_ptr[r + 1]]
+                assert np.all((rows >= 0) & (rows < q1 - q0)) and np.all(np.diff(rows) > 0)
+                received[r][dst_off[r]:dst_off[r] + len(rows)] = x[q0 + rows]   # the "push"
+        for r in range(world):
+            np.testing.assert_array_equal(received[r], x[ghosts[r]])          # every slot filled
