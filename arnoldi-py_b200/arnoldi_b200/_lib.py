@@ -12,11 +12,15 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("AB200_LIB_PATH") or os.path.join(_HERE, "libarnoldi_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 OK, EINVAL, ECUDA, ENOMEM, ESTATE, ECOMM = 0, -1, -2, -3, -4, -5
 F64, C128 = 0, 1
 ORTHO_CGS2, ORTHO_MGS = 0, 1
 SPMV_AUTO, SPMV_VECTOR, SPMV_STREAM, SPMV_MERGE = 0, 1, 2, 3
+SPMV_ALGOS = {"auto": SPMV_AUTO, "vector": SPMV_VECTOR, "stream": SPMV_STREAM, "merge": SPMV_MERGE}
+# C callback type of ab200_set_operator: int fn(void *user, const void *x, void *y, int64 n,
+#                                              int is_real, void *stream)
+APPLY_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p)
 
 
 class Stats(C.Structure):
@@ -53,15 +57,21 @@ SIGNATURES = {
     "ab200_create": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int]),
     "ab200_destroy": (C.c_int, [_P]),
     "ab200_set_csr": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, C.c_int64, C.c_int]),
+    "ab200_set_operator": (C.c_int, [_P, _P, _P, C.c_int]),
     "ab200_set_columns": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int64]),
     "ab200_get_columns": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int64]),
     "ab200_expand": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, _P, _I, _I]),
     "ab200_restart": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int]),
+    "ab200_combine": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, C.c_int]),
+    "ab200_orthonormalize_column": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, C.c_double,
+                                              C.c_int, _D, _I]),
+    "ab200_project": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "ab200_spmv": (C.c_int, [_P, _P, _P]),
     "ab200_ortho": (C.c_int, [_P, C.c_int, _P, _P, C.c_double, C.c_double, C.c_int, _D, _I]),
     "ab200_comm_export": (C.c_int, [_P, _P]),
     "ab200_comm_connect": (C.c_int, [_P, C.c_int, C.c_int, C.c_char_p, _P]),
     "ab200_set_halo": (C.c_int, [_P, _P, C.c_int64]),
+    "ab200_comm_disconnect": (C.c_int, [_P]),
     "ab200_halo_export": (C.c_int, [_P, _P]),
     "ab200_halo_connect": (C.c_int, [_P, C.c_char_p, _P, _P, _P]),
     "ab200_set_timing": (C.c_int, [_P, C.c_int]),
@@ -71,6 +81,8 @@ SIGNATURES = {
     "ab200_timer_start": (C.c_int, [_P]),
     "ab200_timer_stop": (C.c_int, [_P, _D]),
     "ab200_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
+    "ab200_host_schur": (C.c_int, [_P, C.c_int, _P, _P, _P]),
+    "ab200_host_reorder": (C.c_int, [_P, C.c_int, _P, _P, _P, _P]),
     "ab200_host_alloc": (C.c_int, [C.POINTER(_P), C.c_int64]),
     "ab200_host_free": (C.c_int, [_P]),
 }

@@ -159,3 +159,32 @@ def powerlaw(n, **kw):
     """The whole operator as a scipy CSR matrix (small n: tests, single-GPU runs)."""
     b = powerlaw_rows(n, 0, n, **kw)
     return sp.csr_matrix((b.data, b.indices, b.indptr), shape=(n, n))
+
+
+def lap2d_rect(nx, ny, wx=1.0, wy=0.75):
+    """Anisotropic 5-point Laplacian on an ny x nx grid (row-major, x fastest):
+    ``wy * kron(T_ny, I_nx) + wx * kron(I_ny, T_nx)``, T = tridiag(-1, 2, -1).
+
+    Same sparsity, symmetry and real storage as ``lap2d`` but its eigenvalues
+    ``wx (2 - 2 cos(i pi / (nx+1))) + wy (2 - 2 cos(j pi / (ny+1)))`` are simple when
+    nx != ny and wx != wy, so restart counts and Ritz values of a Krylov-Schur solve are not
+    decided by rounding noise (the square isotropic grid has double eigenvalues).  Used to pin
+    config-2-family parity; sorted CSR, float64."""
+    n = nx * ny
+    idx = np.arange(n)
+    gi, gj = idx // nx, idx % nx
+    keep = np.stack([gi > 0, gj > 0, np.ones(n, bool), gj < nx - 1, gi < ny - 1], axis=1)
+    counts = keep.sum(axis=1)
+    indptr = np.concatenate(([0], np.cumsum(counts)))
+    it = _index_dtype(int(indptr[-1]), n)
+    cols = np.stack([idx - nx, idx - 1, idx, idx + 1, idx + nx], axis=1).astype(it)[keep]
+    d = 2.0 * wx + 2.0 * wy
+    vals = np.broadcast_to(np.array([-wy, -wx, d, -wx, -wy]), (n, 5))[keep]
+    return sp.csr_matrix((vals, cols, indptr.astype(it)), shape=(n, n))
+
+
+def lap2d_rect_eigenvalues(nx, ny, wx=1.0, wy=0.75):
+    """All eigenvalues of ``lap2d_rect`` (unsorted)."""
+    cx = 2 - 2 * np.cos(np.arange(1, nx + 1) * np.pi / (nx + 1))
+    cy = 2 - 2 * np.cos(np.arange(1, ny + 1) * np.pi / (ny + 1))
+    return (wy * cy[:, None] + wx * cx[None, :]).ravel()

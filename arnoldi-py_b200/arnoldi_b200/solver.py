@@ -48,6 +48,9 @@ class DeviceSolver:
     # -- operator ---------------------------------------------------------------
     def set_csr(self, indptr, indices, data, *, algo=_lib.SPMV_AUTO):
         """Upload a CSR row block exactly as scipy stores it (no re-ordering)."""
+        if isinstance(algo, str):
+            assert algo in _lib.SPMV_ALGOS, f"spmv_algo must be one of {sorted(_lib.SPMV_ALGOS)}"
+            algo = _lib.SPMV_ALGOS[algo]
         indptr = np.ascontiguousarray(indptr)
         if indptr.dtype not in (np.int32, np.int64):
             indptr = indptr.astype(np.int64)
@@ -64,6 +67,24 @@ class DeviceSolver:
                                           _ptr(indices), _ptr(data), kind, int(data.shape[0]),
                                           int(algo)))
         self.nnz = int(data.shape[0])
+        self.value_kind = kind
+
+    def set_operator(self, op):
+        """Use a device operator (``device_operator.DeviceOperator`` protocol) instead of CSR:
+        ``op.device_apply(x_ptr, y_ptr, n, is_real, stream_ptr)`` must enqueue ``y = A x`` on
+        the given CUDA stream.  The callback object is kept alive by this solver."""
+        def trampoline(_user, x, y, n, is_real, stream):
+            try:
+                op.device_apply(int(x), int(y), int(n), bool(is_real), int(stream or 0))
+                return 0
+            except Exception:      # an exception cannot cross the C frame
+                import traceback
+                traceback.print_exc()
+                return 1
+        self._op_cb = _lib.APPLY_FN(trampoline)
+        kind = _lib.C128 if np.dtype(op.dtype).kind == "c" else _lib.F64
+        _lib.check(self.lib.ab200_set_operator(self._h, C.cast(self._op_cb, C.c_void_p), None, kind))
+        self.nnz = 0
         self.value_kind = kind
 
     # -- basis ------------------------------------------------------------------
@@ -117,6 +138,26 @@ class DeviceSolver:
         q = np.asfortranarray(Q[:m, :p], dtype=np.complex128)
         _lib.check(self.lib.ab200_restart(self._h, _ptr(q), int(m), int(m), int(p)))
 
+    def combine(self, Q, col0, m, p):
+        """V[:, col0:col0+p] = V[:, col0:col0+m] Q[:m, :p]; no other column is touched."""
+        q = np.asfortranarray(np.asarray(Q)[:m, :p], dtype=np.complex128)
+        _lib.check(self.lib.ab200_combine(self._h, _ptr(q), int(m), int(col0), int(m), int(p)))
+
+    def orthonormalize_column(self, col, ncols, tol, *, eta=np.sqrt(0.5), ortho=_lib.ORTHO_CGS2):
+        """Orthonormalise basis column ``col`` against columns [0, ncols) on the device;
+        returns its norm after the projections (below ``tol``: left un-normalised)."""
+        beta, brk = C.c_double(0.0), C.c_int(0)
+        _lib.check(self.lib.ab200_orthonormalize_column(self._h, int(col), int(ncols), float(tol),
+                                                        float(eta), int(ortho), C.byref(beta),
+                                                        C.byref(brk)))
+        return beta.value
+
+    def project(self, col, nrows):
+        """h[i] = <V_i, A V_col> for i < nrows (explicit_restarts.py:150-151)."""
+        h = np.empty(nrows, np.complex128)
+        _lib.check(self.lib.ab200_project(self._h, int(col), int(nrows), _ptr(h)))
+        return h
+
     def spmv(self, x):
         x = np.ascontiguousarray(x, dtype=np.complex128)
         assert x.shape == (self.n_global,)
@@ -142,6 +183,11 @@ class DeviceSolver:
         _lib.check(self.lib.ab200_comm_connect(self._h, int(comm.rank), int(comm.world), blobs,
                                                _ptr(starts)))
         comm.barrier()
+
+    def disconnect(self):
+        """First half of the multi-GPU teardown (unmap the peers); follow with a barrier."""
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _lib.check(self.lib.ab200_comm_disconnect(self._h))
 
     def set_halo(self, ghost_cols):
         g = np.ascontiguousarray(ghost_cols, dtype=np.int64)
@@ -175,6 +221,10 @@ class DeviceSolver:
         st = _lib.Stats()
         _lib.check(self.lib.ab200_get_stats(self._h, C.byref(st)))
         return st.as_dict()
+
+    def true_matvecs(self):
+        """Operator applications since the last reset (device-side counter)."""
+        return int(self.stats()["arnoldi_steps"])
 
     def synchronize(self):
         _lib.check(self.lib.ab200_synchronize(self._h))

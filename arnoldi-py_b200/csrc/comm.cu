@@ -77,10 +77,11 @@ __global__ void halo_wait_kernel(const unsigned long long* hflags, unsigned need
   const int q = threadIdx.x;
   if (q < kMaxRanks && ((need_mask >> q) & 1u)) {
     volatile const unsigned long long* f = hflags + q;
-    long long spins = 0;
+    const unsigned long long t0 = global_ns();
+    unsigned spins = 0;
     while (*f < seq) {
-      if (++spins > (1ll << 26)) {
-        if (ctl) ctl->comm_error = 1;
+      if ((++spins & 0x3ffu) == 0 && global_ns() - t0 > kPeerTimeoutNs) {
+        if (ctl) ctl->comm_error = 1, ctl->stop = 1;
         break;
       }
     }

@@ -15,6 +15,15 @@ typedef double2 cplx;  // .x = re, .y = im
 
 constexpr int kWarp = 32;
 constexpr int kNumSMsB200 = 148;
+constexpr int kMaxDim = 256;        // basis columns a solver may hold (ab200_create)
+constexpr int kPass1MaxCols = 128;  // columns one CGS pass-1 / fused launch covers (16 warps x 8)
+constexpr unsigned long long kPeerTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
+
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 // ---------------------------------------------------------------- loads / stores
 // Streaming 128-bit load of read-only data that is touched once per kernel

@@ -14,10 +14,14 @@ struct OrthoArgs {
   int64_t ld;        // leading dimension of U in 16-byte elements
   int real;          // basis stored real: an element is two consecutive real rows
   int ncols;         // c = number of basis columns to orthogonalise against
+  int p1_col0;       // pass 1 only: this launch covers columns [p1_col0, p1_col0 + p1_ncols)
+  int p1_ncols;      //   (c > 128 is swept in column groups of at most 128)
   int j;             // Arnoldi step (H column) -- ncols - 1 inside an expansion
   int round;         // 1 or 2 (DGKS repeat)
   int accumulate;    // h += (round 2) instead of h =
-  int finalize;      // write H[j+1, j], scale[j+1], breakdown flag when the step ends
+  int finalize;      // 1: write H[j+1, j], scale[j+1], breakdown flag when the step ends and count
+                     //    an Arnoldi step; 2: the same without counting (a column normalised
+                     //    outside an expansion); 0: nothing
   int grid_cap;      // capacity (in blocks) of the partial buffers
   int stages;        // cp.async staging depth of the fused sweep (0 = automatic)
   int fused_r;       // rows pairs per lane and chunk in the fused sweep (0 = automatic)
@@ -41,7 +45,7 @@ cudaError_t launch_cgs_pass2(const OrthoArgs& a, int num_sms, cudaStream_t st, i
 cudaError_t launch_mgs_step(const OrthoArgs& a, int i, int num_sms, cudaStream_t st,
                             int grid_mult);
 
-cudaError_t launch_peer_barrier(const PeerComm& pc, StepCtl* ctl, cudaStream_t st);
+cudaError_t launch_peer_barrier(const PeerComm& pc, StepCtl* ctl, int real_mode, cudaStream_t st);
 
 // ---------------------------------------------------------------- SpMV
 struct SpmvArgs {
@@ -60,9 +64,21 @@ struct SpmvArgs {
   int tile;                // nnz staged per block iteration
   int threads;             // block size: 128 or 256
   int long_rows;           // some row has more than 16 entries: warp-per-row path compiled in
-  int variant;             // 0 = streaming (cp.async, persistent) kernel when no long rows; 1 = plain
+  int variant;             // 0 = bulk-copy (TMA) pipeline when no long rows; 1 = plain tile kernel;
+                           // 2 = cp.async streaming kernel (round-1 default, kept for A/B)
   int num_sms;
   const StepCtl* ctl;      // nullptr for the stand-alone entry point
+  // bulk-copy pipeline shape (spmv_bulk_kernel)
+  int stages;              // shared-memory ring depth
+  int rp_cap;              // row pointers staged per tile (multiple of 4)
+  int bps;                 // resident blocks per SM to launch (0 = what fits)
+  // halo read straight from the owners' HBM (multi-GPU "pull"): ghost entry g of rank q lives at
+  // peer_col[q][ghost_off[g]]; entries [seg_start[q], seg_start[q+1]) belong to rank q
+  int direct_halo;
+  int nranks;
+  const void* peer_col[kMaxRanks];
+  int64_t seg_start[kMaxRanks + 1];
+  const int64_t* ghost_off;
 };
 
 cudaError_t launch_spmv(const SpmvArgs& a, int indptr_bits, int value_kind, cudaStream_t st);
@@ -107,7 +123,8 @@ cudaError_t launch_halo_wait(const unsigned long long* hflags, unsigned need_mas
 
 // ---------------------------------------------------------------- restart + helpers
 struct RestartArgs {
-  cplx* U;              // basis, updated in place
+  int copy_tail;        // 1: also U[:, p] = scale_m * U[:, m] (a restart); 0: plain U[:, :p] = U[:, :m] q
+  cplx* U;              // basis (first of the m input columns), updated in place
   int64_t n, ld;
   int m, p;
   const cplx* q;        // device copy of Q[:, :p], row i pre-multiplied by scale[i]; layout [i * p + k]
@@ -115,6 +132,10 @@ struct RestartArgs {
   int real;             // basis stored real: n, ld count pairs of rows and q is real (.x)
 };
 cudaError_t launch_restart(const RestartArgs& a, int num_sms, cudaStream_t st, int variant);
+
+// y = (*scale) * x over n 16-byte elements (device-operator path: the operator sees v_j itself)
+cudaError_t launch_scaled_copy(const cplx* x, cplx* y, int64_t n, const double* scale, int real,
+                               int num_sms, cudaStream_t st);
 
 cudaError_t launch_pack_real(const cplx* src, double* dst, int64_t n, int num_sms, cudaStream_t st);
 cudaError_t launch_unpack_real(const double* src, cplx* dst, int64_t n, double scale, int num_sms,

@@ -55,13 +55,16 @@ __device__ void peer_allreduce(const PeerComm& pc, double* red, int count, StepC
     volatile unsigned long long* f = pc.flags[tid] + (size_t)par * kMaxRanks + pc.rank;
     *f = seq;
   }
-  // 3. wait for every rank's flag in my own flag array
+  // 3. wait for every rank's flag in my own flag array (wall-clock bound: a peer that died or
+  //    diverged must not hang the box; on timeout every later kernel becomes a no-op)
   if (tid < pc.nranks) {
     volatile unsigned long long* f = pc.flags[pc.rank] + (size_t)par * kMaxRanks + tid;
-    long long spins = 0;
+    const unsigned long long t0 = global_ns();
+    unsigned spins = 0;
     while (*f < seq) {
-      if (++spins > (1ll << 26)) {  // ~tens of seconds: a peer died or diverged
+      if ((++spins & 0x3ffu) == 0 && global_ns() - t0 > kPeerTimeoutNs) {
         ctl->comm_error = 1;
+        ctl->stop = 1;
         break;
       }
     }
@@ -98,7 +101,7 @@ __device__ void finish_dots(const OrthoArgs& a, int col0, int ncols, double* red
 __device__ void finalize_step(const OrthoArgs& a, double beta) {
   StepCtl* ctl = a.ctl;
   if (!a.finalize) return;
-  ctl->steps_total += 1;
+  if (a.finalize == 1) ctl->steps_total += 1;  // 2 = normalise a column outside an Arnoldi step
   if (beta < a.tol) {  // ortho.py:107, decomposition.py:61-63
     ctl->stop = 1;
     ctl->broke_at = a.j;
@@ -149,13 +152,13 @@ __global__ void __launch_bounds__(CT < 8 ? 256 : 512) cgs_pass1_kernel(OrthoArgs
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const int c = a.ncols;
+  const int c = a.p1_ncols;  // columns [p1_col0, p1_col0 + c) of the basis
   const int mycol0 = warp * CT;
   int mycols = c - mycol0;
   mycols = mycols < 0 ? 0 : (mycols > CT ? CT : mycols);
   const int64_t ld = a.ld;
   const cplx* __restrict__ w = a.w;
-  const cplx* __restrict__ U = a.U + (int64_t)mycol0 * ld;
+  const cplx* __restrict__ U = a.U + (int64_t)(a.p1_col0 + mycol0) * ld;
 
   cplx acc[CT];
 #pragma unroll
@@ -246,7 +249,7 @@ __global__ void __launch_bounds__(CT < 8 ? 256 : 512) cgs_pass1_kernel(OrthoArgs
   __syncthreads();
   peer_allreduce(a.comm, red, 2 * c + 1, ctl);
   __syncthreads();
-  finish_dots(a, 0, c, red, a.round == 1);
+  finish_dots(a, a.p1_col0, c, red, a.round == 1 && a.p1_col0 == 0);
 }
 
 // ------------------------------------------------------------------ CGS pass 2
@@ -834,16 +837,23 @@ __global__ void __launch_bounds__(256) mgs_step_kernel(OrthoArgs a, int i) {
 // All ranks' streams meet here: everything a rank enqueued before this kernel (restart
 // update, column uploads) is complete and visible before any rank runs what follows (the
 // first halo gather of an expansion).  One 32-thread block, one NVLink round trip.
-__global__ void peer_barrier_kernel(PeerComm pc, StepCtl* ctl) {
+// The token carries this rank's storage mode: the ranks must agree on it (halo reads use the
+// reader's element size on the owner's memory), so a mixed sum is a communicator error.
+__global__ void peer_barrier_kernel(PeerComm pc, StepCtl* ctl, int real_mode) {
   __shared__ double token[1];
-  if (threadIdx.x == 0) token[0] = 1.0;
+  if (threadIdx.x == 0) token[0] = real_mode ? 1.0 : 0.0;
   __syncthreads();
   __threadfence_system();
   peer_allreduce(pc, token, 1, ctl);
+  __syncthreads();
+  if (threadIdx.x == 0 && token[0] != 0.0 && token[0] != (double)pc.nranks) {
+    ctl->comm_error = 2;
+    ctl->stop = 1;
+  }
 }
-cudaError_t launch_peer_barrier(const PeerComm& pc, StepCtl* ctl, cudaStream_t st) {
+cudaError_t launch_peer_barrier(const PeerComm& pc, StepCtl* ctl, int real_mode, cudaStream_t st) {
   if (pc.nranks <= 1) return cudaSuccess;
-  peer_barrier_kernel<<<1, 32, 0, st>>>(pc, ctl);
+  peer_barrier_kernel<<<1, 32, 0, st>>>(pc, ctl, real_mode);
   return cudaGetLastError();
 }
 
@@ -877,7 +887,7 @@ static cudaError_t launch_pass1_tr(const OrthoArgs& a, int warps, int num_sms, c
   OrthoArgs args = a;
   const int threads = warps * kWarp;
   const int64_t nchunks = (a.n + kWarp * R - 1) / (kWarp * R);
-  const size_t smem = sizeof(double) * (2 * a.ncols + 2);
+  const size_t smem = sizeof(double) * (2 * a.p1_ncols + 2);
   static int occ[17] = {0};
   const int bps = grid_mult > 0 ? grid_mult
                                 : resident_blocks(cgs_pass1_kernel<CT, R, REAL>, threads, smem, &occ[warps]);
@@ -892,9 +902,10 @@ static cudaError_t launch_pass1_t(const OrthoArgs& a, int warps, int num_sms, cu
                 : launch_pass1_tr<CT, R, false>(a, warps, num_sms, st, grid_mult);
 }
 
-cudaError_t launch_cgs_pass1(const OrthoArgs& a, int num_sms, cudaStream_t st, int grid_mult) {
+static cudaError_t launch_pass1_group(const OrthoArgs& a, int num_sms, cudaStream_t st,
+                                      int grid_mult) {
   int ct, warps;
-  pass1_shape(a.ncols, &ct, &warps);
+  pass1_shape(a.p1_ncols, &ct, &warps);
   if (warps > 16) return cudaErrorInvalidValue;
   switch (ct) {
     case 1: return launch_pass1_t<1, 4>(a, warps, num_sms, st, grid_mult);
@@ -906,6 +917,22 @@ cudaError_t launch_cgs_pass1(const OrthoArgs& a, int num_sms, cudaStream_t st, i
     case 7: return launch_pass1_t<7, 2>(a, warps, num_sms, st, grid_mult);
     default: return launch_pass1_t<8, 2>(a, warps, num_sms, st, grid_mult);
   }
+}
+
+// One launch covers at most 128 columns (16 warps x 8 columns); wider bases are swept in
+// balanced column groups, each with its own reduction (the norm rides on the first group).
+cudaError_t launch_cgs_pass1(const OrthoArgs& a, int num_sms, cudaStream_t st, int grid_mult) {
+  const int c = a.ncols;
+  const int groups = (c + kPass1MaxCols - 1) / kPass1MaxCols;
+  const int per = (c + groups - 1) / groups;
+  for (int col0 = 0; col0 < c; col0 += per) {
+    OrthoArgs g = a;
+    g.p1_col0 = col0;
+    g.p1_ncols = c - col0 < per ? c - col0 : per;
+    cudaError_t e = launch_pass1_group(g, num_sms, st, grid_mult);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
 }
 
 // resident blocks per SM for a kernel / block shape (cached: the query costs microseconds)

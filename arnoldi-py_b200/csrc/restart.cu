@@ -41,6 +41,7 @@ __global__ void __launch_bounds__(512) restart_kernel(RestartArgs a) {
   const int64_t ld = a.ld;
   const int64_t nchunks = (a.n + kWarp - 1) / kWarp;
   constexpr int B = 4;  // columns per load batch; two batches are in flight
+  const int mlast = a.copy_tail ? m : m - 1;
 
   for (int64_t q = blockIdx.x; q < nchunks; q += gridDim.x) {
     const int64_t row = q * kWarp + lane;
@@ -56,7 +57,8 @@ __global__ void __launch_bounds__(512) restart_kernel(RestartArgs a) {
 #pragma unroll
       for (int t = 0; t < B; ++t) {
         const int col = i + B + t;
-        nxt[t] = ld_pinned(src + (int64_t)(col < m ? col : m) * ld);  // column m is read anyway
+        // past the end: column m (read for the tail anyway) or, without a tail, column m - 1 again
+        nxt[t] = ld_pinned(src + (int64_t)(col < m ? col : mlast) * ld);
       }
 #pragma unroll
       for (int t = 0; t < B; ++t) {
@@ -71,14 +73,14 @@ __global__ void __launch_bounds__(512) restart_kernel(RestartArgs a) {
       for (int t = 0; t < B; ++t) cur[t] = nxt[t];
     }
     cplx tail = make_double2(0.0, 0.0);
-    if (wy == 0) tail = cscale(ld_pinned(src + (int64_t)m * ld), a.scale_m);
+    if (wy == 0 && a.copy_tail) tail = cscale(ld_pinned(src + (int64_t)m * ld), a.scale_m);
     if (blockDim.x > kWarp) __syncthreads();  // every warp of the block has read these rows
     if (ok) {
       cplx* dst = a.U + row;
 #pragma unroll
       for (int k = 0; k < PT; ++k)
         if (k < nk) st_stream(dst + (int64_t)(k0 + k) * ld, acc[k]);
-      if (wy == 0) st_stream(dst + (int64_t)p * ld, tail);
+      if (wy == 0 && a.copy_tail) st_stream(dst + (int64_t)p * ld, tail);
     }
   }
 }
@@ -186,6 +188,24 @@ cudaError_t launch_unpack_real(const double* src, cplx* dst, int64_t n, double s
   if (grid > (int64_t)num_sms * 8) grid = (int64_t)num_sms * 8;
   if (grid < 1) grid = 1;
   unpack_real_kernel<<<(int)grid, 256, 0, st>>>(src, dst, n, scale);
+  return cudaGetLastError();
+}
+
+// y = (*scale) * x : the device-operator path hands the operator the true v_j = s_j U_j
+__global__ void __launch_bounds__(256) scaled_copy_kernel(const cplx* __restrict__ x, cplx* __restrict__ y,
+                                                          int64_t n, const double* scale) {
+  const double s = scale ? *scale : 1.0;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n;
+       r += (int64_t)gridDim.x * blockDim.x)
+    st_stream(y + r, cscale(ld_stream(x + r), s));
+}
+cudaError_t launch_scaled_copy(const cplx* x, cplx* y, int64_t n, const double* scale, int real,
+                               int num_sms, cudaStream_t st) {
+  (void)real;  // n counts 16-byte elements in both storage modes
+  int64_t grid = (n + 255) / 256;
+  if (grid > (int64_t)num_sms * 8) grid = (int64_t)num_sms * 8;
+  if (grid < 1) grid = 1;
+  scaled_copy_kernel<<<(int)grid, 256, 0, st>>>(x, y, n, scale);
   return cudaGetLastError();
 }
 

@@ -12,6 +12,7 @@
 #include <string.h>
 
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/arnoldi_b200.h"
@@ -92,7 +93,12 @@ struct ab200_solver {
   int nblk = 0;
   int tile = 0;
   int spmv_threads = 128;
+  int spmv_algo = AB200_SPMV_AUTO;
+  int spmv_stages = 3, spmv_rp_cap = 0;
   int max_row_len = 0;
+  // user-supplied device operator (ab200_set_operator) instead of a CSR block
+  ab200_apply_fn op_fn = nullptr;
+  void* op_user = nullptr;
   cplx* ghost = nullptr;
   int64_t n_local_cols = 0;
 
@@ -123,7 +129,14 @@ struct ab200_solver {
 
   // options
   int opt_grid_mult = 0, opt_restart_variant = 0, opt_ortho_variant = 0, opt_spmv_tile = 0,
-      opt_fused_ct = 0, opt_spmv_threads = 0, opt_fused_stages = 0, opt_fused_r = 0, opt_spmv_variant = 0;
+      opt_fused_ct = 0, opt_spmv_threads = 0, opt_fused_stages = 0, opt_fused_r = 0, opt_spmv_variant = 0,
+      opt_spmv_stages = 0, opt_spmv_bps = 0, opt_halo_fold = 1;
+  bool disconnected = false;
+  // download path: two pinned bounce buffers + a copy stream (ab200_get_columns)
+  void* bounce[2] = {nullptr, nullptr};
+  size_t bounce_bytes = 0;
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t bounce_ev[2] = {nullptr, nullptr};
 
   // stats
   bool timing = false;
@@ -276,6 +289,8 @@ static OrthoArgs make_ortho_args(ab200_solver* s, cplx* w, int ncols, int j, dou
   a.n = s->real_mode ? (s->n + 1) / 2 : s->n;
   a.ld = s->real_mode ? s->ld / 2 : s->ld;
   a.ncols = ncols;
+  a.p1_col0 = 0;
+  a.p1_ncols = ncols;
   a.j = j;
   a.round = 1;
   a.accumulate = 0;
@@ -301,7 +316,8 @@ static OrthoArgs make_ortho_args(ab200_solver* s, cplx* w, int ncols, int j, dou
 static int enqueue_ortho(ab200_solver* s, OrthoArgs a, int ortho_kind) {
   const double nb = elem_bytes(s) * (double)s->n;
   const int c = a.ncols;
-  const bool fuse = s->opt_ortho_variant == 0 ? s->dgks_hot : s->opt_ortho_variant != 1;
+  const bool fuse = (s->opt_ortho_variant == 0 ? s->dgks_hot : s->opt_ortho_variant != 1) &&
+                    c <= kPass1MaxCols;  // the fused sweep holds all c columns in one block
   if (ortho_kind == AB200_ORTHO_CGS2 && fuse) {
     // default CGS2/DGKS schedule: 3 sweeps when the DGKS test fires, 2 when it does not
     a.round = 1;
@@ -360,6 +376,25 @@ int ab200_device_count(void) {
   return n;
 }
 
+// Close every mapping of peer memory.  Multi-GPU teardown is two-phase: every rank disconnects,
+// the ranks meet (host barrier), and only then ab200_destroy frees the buffers the peers had
+// mapped -- freeing an exported allocation while an importer still maps it is undefined.
+int ab200_comm_disconnect(ab200_solver* s) {
+  REQUIRE(s != nullptr, "solver is null");
+  CU(cudaSetDevice(s->device));
+  if (s->stream) CU(cudaStreamSynchronize(s->stream));
+  for (int r = 0; r < kMaxRanks; ++r) {
+    if (s->peer_V[r]) cudaIpcCloseMemHandle(s->peer_V[r]);
+    if (s->peer_slots[r]) cudaIpcCloseMemHandle(s->peer_slots[r]);
+    if (s->peer_flags[r]) cudaIpcCloseMemHandle(s->peer_flags[r]);
+    if (s->peer_ghost[r]) cudaIpcCloseMemHandle(s->peer_ghost[r]);
+    if (s->peer_hflags[r]) cudaIpcCloseMemHandle(s->peer_hflags[r]);
+    s->peer_V[r] = s->peer_slots[r] = s->peer_flags[r] = s->peer_ghost[r] = s->peer_hflags[r] = nullptr;
+  }
+  if (s->nranks > 1) s->disconnected = true;  // no further multi-GPU work on this handle
+  return AB200_OK;
+}
+
 int ab200_destroy(ab200_solver* s) {
   if (!s) return AB200_OK;
   cudaSetDevice(s->device);
@@ -367,22 +402,24 @@ int ab200_destroy(ab200_solver* s) {
   resolve_pending(s, nullptr);
   for (auto e : s->pool) cudaEventDestroy(e);
   if (s->t0) cudaEventDestroy(s->t0), cudaEventDestroy(s->t1);
+  // imports first (a no-op after ab200_comm_disconnect), then the buffers this rank owns
+  for (int r = 0; r < kMaxRanks; ++r) {
+    if (s->peer_V[r]) cudaIpcCloseMemHandle(s->peer_V[r]);
+    if (s->peer_slots[r]) cudaIpcCloseMemHandle(s->peer_slots[r]);
+    if (s->peer_flags[r]) cudaIpcCloseMemHandle(s->peer_flags[r]);
+    if (s->peer_ghost[r]) cudaIpcCloseMemHandle(s->peer_ghost[r]);
+    if (s->peer_hflags[r]) cudaIpcCloseMemHandle(s->peer_hflags[r]);
+  }
   cudaFree(s->V), cudaFree(s->wtmp), cudaFree(s->xtmp), cudaFree(s->scale), cudaFree(s->Hdev);
   cudaFree(s->hscratch), cudaFree(s->coef), cudaFree(s->part), cudaFree(s->npart);
   cudaFree(s->ticket), cudaFree(s->ctl), cudaFree(s->step_round2), cudaFree(s->qdev);
   cudaFree(s->indptr), cudaFree(s->indices), cudaFree(s->values), cudaFree(s->rowblk);
   cudaFree(s->ghost), cudaFree(s->ghost_off);
-  for (int r = 0; r < kMaxRanks; ++r) {
-    if (s->peer_V[r]) cudaIpcCloseMemHandle(s->peer_V[r]);
-    if (s->peer_slots[r]) cudaIpcCloseMemHandle(s->peer_slots[r]);
-    if (s->peer_flags[r]) cudaIpcCloseMemHandle(s->peer_flags[r]);
-  }
   cudaFree(s->slots), cudaFree(s->flags), cudaFree(s->seq);
-  for (int r = 0; r < kMaxRanks; ++r) {
-    if (s->peer_ghost[r]) cudaIpcCloseMemHandle(s->peer_ghost[r]);
-    if (s->peer_hflags[r]) cudaIpcCloseMemHandle(s->peer_hflags[r]);
-  }
   cudaFree(s->hflags), cudaFree(s->send_idx), cudaFree(s->push_ticket);
+  if (s->bounce[0]) cudaFreeHost(s->bounce[0]);
+  if (s->bounce[1]) cudaFreeHost(s->bounce[1]);
+  if (s->stream2) cudaStreamDestroy(s->stream2);
   cudaFreeHost(s->h_H), cudaFreeHost(s->h_scale), cudaFreeHost(s->h_ctl);
   cudaFreeHost(s->h_step_round2), cudaFreeHost(s->h_q);
   if (s->stream) cudaStreamDestroy(s->stream);
@@ -397,7 +434,7 @@ int ab200_create(ab200_solver** out, int device, int64_t n_global, int64_t row0,
   REQUIRE(n_global > 0 && nrows_local > 0 && row0 >= 0 && row0 + nrows_local <= n_global,
           "bad row block: n_global=%lld row0=%lld nrows_local=%lld", (long long)n_global,
           (long long)row0, (long long)nrows_local);
-  REQUIRE(max_dim >= 1 && max_dim <= 128, "max_dim must be in [1, 128], got %d", max_dim);
+  REQUIRE(max_dim >= 1 && max_dim <= kMaxDim, "max_dim must be in [1, %d], got %d", kMaxDim, max_dim);
   int ndev = 0;
   CU(cudaGetDeviceCount(&ndev));
   REQUIRE(device >= 0 && device < ndev, "device %d not available (%d visible)", device, ndev);
@@ -490,17 +527,23 @@ int ab200_set_csr(ab200_solver* s, const void* indptr, int indptr_bits, const in
   cudaFree(s->indptr), cudaFree(s->indices), cudaFree(s->values), cudaFree(s->rowblk);
   s->indptr = s->indices = nullptr, s->values = nullptr, s->rowblk = nullptr;
   s->nnz = -1;
+  s->op_fn = nullptr;
   const size_t ipb = (size_t)indptr_bits / 8, vb = value_kind == AB200_F64 ? 8 : 16;
-  CU(cudaMalloc(&s->indptr, ipb * (s->n + 1)));
-  CU(cudaMalloc(&s->indices, sizeof(int32_t) * (size_t)(nnz + 4)));
-  CU(cudaMalloc(&s->values, vb * (size_t)(nnz + 4)));
+  // spare entries: the SpMV stages whole 16-byte groups (4 column ids / values, 4 or 2 row
+  // pointers), so every array may be read a little past its end
+  CU(cudaMalloc(&s->indptr, ipb * (s->n + 1 + 8)));
+  CU(cudaMalloc(&s->indices, sizeof(int32_t) * (size_t)(nnz + 8)));
+  CU(cudaMalloc(&s->values, vb * (size_t)(nnz + 8)));
+  CU(cudaMemsetAsync(static_cast<char*>(s->indptr) + ipb * (s->n + 1), 0, ipb * 8, s->stream));
+  CU(cudaMemsetAsync(s->indices + nnz, 0, sizeof(int32_t) * 8, s->stream));
+  CU(cudaMemsetAsync(static_cast<char*>(s->values) + vb * (size_t)nnz, 0, vb * 8, s->stream));
   CU(cudaMemcpyAsync(s->indptr, indptr, ipb * (s->n + 1), cudaMemcpyHostToDevice, s->stream));
   if (nnz > 0) {
     CU(cudaMemcpyAsync(s->indices, indices, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice,
                        s->stream));
     CU(cudaMemcpyAsync(s->values, values, vb * (size_t)nnz, cudaMemcpyHostToDevice, s->stream));
   }
-  // longest row decides whether the SpMV needs its warp-per-row path at all
+  // longest row decides which kernels apply
   CU(cudaMemsetAsync(s->ticket, 0, sizeof(unsigned), s->stream));
   CU(launch_spmv_maxrow(s->indptr, indptr_bits, s->n, reinterpret_cast<int*>(s->ticket), s->stream));
   int maxrow = 0;
@@ -508,18 +551,29 @@ int ab200_set_csr(ab200_solver* s, const void* indptr, int indptr_bits, const in
   CU(cudaStreamSynchronize(s->stream));
   CU(cudaMemsetAsync(s->ticket, 0, sizeof(unsigned), s->stream));
   s->max_row_len = maxrow;
-  // nnz tile: about one row per thread of the block, within [512, 2048]
-  const int threads = s->opt_spmv_threads == 256 ? 256 : 128;  // 128 measured 3% faster
+  // AB200_SPMV_STREAM is the one-thread-per-row pipeline: it needs short rows
+  if (spmv_algo == AB200_SPMV_STREAM && maxrow > 16)
+    return set_err(AB200_EINVAL,
+                   "AB200_SPMV_STREAM needs rows of at most 16 entries (longest row: %d); use "
+                   "AB200_SPMV_VECTOR, AB200_SPMV_MERGE or AB200_SPMV_AUTO", maxrow);
+  s->spmv_algo = spmv_algo;
+  const bool short_rows = maxrow <= 16 && spmv_algo != AB200_SPMV_VECTOR && spmv_algo != AB200_SPMV_MERGE;
+  // nnz tile: about one row per thread of the block, within [512, 4096]
+  int threads = short_rows ? 256 : 128;
+  if (s->opt_spmv_threads == 128 || s->opt_spmv_threads == 256) threads = s->opt_spmv_threads;
   int tile = s->opt_spmv_tile;
   if (tile <= 0) {
     double avg = (double)nnz / (double)s->n;
     tile = (int)(avg * threads);
     tile = (tile + 127) / 128 * 128;
     if (tile < 512) tile = 512;
-    if (tile > 2048) tile = 2048;
-    if (maxrow > 16 && tile > 1280) tile = 1280;  // skewed rows: measured best on the power-law operator
+    if (tile > 4096) tile = 4096;
+    if (!short_rows && tile > 1280) tile = 1280;  // skewed rows: measured best on the power-law operator
   }
+  tile = (tile + 7) / 8 * 8;
   s->spmv_threads = threads;
+  s->spmv_stages = s->opt_spmv_stages >= 2 && s->opt_spmv_stages <= 8 ? s->opt_spmv_stages : 3;
+  s->spmv_rp_cap = 2 * threads + 8;
   int64_t nblk = (nnz + tile - 1) / tile;
   if (nblk < 1) nblk = 1;
   REQUIRE(nblk < (1ll << 30), "too many SpMV tiles");
@@ -531,6 +585,28 @@ int ab200_set_csr(ab200_solver* s, const void* indptr, int indptr_bits, const in
   s->nnz = nnz;
   s->tile = tile;
   s->nblk = (int)nblk;
+  return AB200_OK;
+}
+
+// A device operator in place of a CSR block: `fn(user, x, y, n, is_real, stream)` must enqueue
+// y = A x on `stream` (device pointers; float64 entries when is_real, else interleaved
+// complex128) and return 0.  The generic-operator row of SURVEY.md section 8f
+// (README.md:119 of the reference: "LinearOperator support").  Single GPU.
+int ab200_set_operator(ab200_solver* s, ab200_apply_fn fn, void* user, int value_kind) {
+  REQUIRE(s != nullptr && fn != nullptr, "null argument");
+  REQUIRE(value_kind == AB200_F64 || value_kind == AB200_C128, "bad value_kind %d", value_kind);
+  if (s->nranks > 1) return set_err(AB200_ESTATE, "device operators are single-GPU");
+  CU(cudaSetDevice(s->device));
+  CU(cudaStreamSynchronize(s->stream));
+  if (value_kind == AB200_C128) {
+    int rc = switch_to_complex(s);
+    if (rc != AB200_OK) return rc;
+  }
+  if (!s->xtmp) CU(cudaMalloc(&s->xtmp, sizeof(cplx) * (size_t)s->ld));
+  s->op_fn = fn;
+  s->op_user = user;
+  s->value_kind = value_kind;
+  s->nnz = 0;  // "an operator is set"
   return AB200_OK;
 }
 
@@ -577,20 +653,78 @@ int ab200_set_columns(ab200_solver* s, int col0, int ncols, const double* host, 
   return AB200_OK;
 }
 
+// Device -> pageable host through two pinned bounce buffers: the D2H copy of chunk i+1 runs
+// while host threads move chunk i out of its bounce buffer (a multi-GB result is otherwise
+// limited by the driver's pageable path and by first-touch page faults on one thread).
+static const size_t kBounceBytes = (size_t)32 << 20;
+static int ensure_bounce(ab200_solver* s) {
+  if (s->bounce[0]) return AB200_OK;
+  CU(cudaMallocHost(&s->bounce[0], kBounceBytes));
+  CU(cudaMallocHost(&s->bounce[1], kBounceBytes));
+  CU(cudaEventCreateWithFlags(&s->bounce_ev[0], cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&s->bounce_ev[1], cudaEventDisableTiming));
+  s->bounce_bytes = kBounceBytes;
+  return AB200_OK;
+}
+static void parallel_copy(char* dst, const char* src, size_t bytes) {
+  const int nt = bytes >= ((size_t)8 << 20) ? 4 : 1;
+  if (nt == 1) {
+    memcpy(dst, src, bytes);
+    return;
+  }
+  std::vector<std::thread> th;
+  const size_t per = (bytes / nt + 4095) & ~(size_t)4095;
+  for (int t = 0; t < nt; ++t) {
+    const size_t o = (size_t)t * per;
+    if (o >= bytes) break;
+    const size_t len = bytes - o < per ? bytes - o : per;
+    th.emplace_back([=] { memcpy(dst + o, src + o, len); });
+  }
+  for (auto& t : th) t.join();
+}
+// stream-ordered device -> host copy of `bytes` from `dev` to pageable `host`
+static int download(ab200_solver* s, char* host, const char* dev, size_t bytes) {
+  if (bytes < ((size_t)4 << 20)) {
+    CU(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return AB200_OK;
+  }
+  int rc = ensure_bounce(s);
+  if (rc != AB200_OK) return rc;
+  const size_t cb = s->bounce_bytes;
+  const size_t nchunk = (bytes + cb - 1) / cb;
+  auto issue = [&](size_t i) -> cudaError_t {
+    const size_t o = i * cb, len = bytes - o < cb ? bytes - o : cb;
+    cudaError_t e = cudaMemcpyAsync(s->bounce[i & 1], dev + o, len, cudaMemcpyDeviceToHost, s->stream);
+    if (e != cudaSuccess) return e;
+    return cudaEventRecord(s->bounce_ev[i & 1], s->stream);
+  };
+  CU(issue(0));
+  for (size_t i = 0; i < nchunk; ++i) {
+    if (i + 1 < nchunk) CU(issue(i + 1));
+    CU(cudaEventSynchronize(s->bounce_ev[i & 1]));
+    const size_t o = i * cb, len = bytes - o < cb ? bytes - o : cb;
+    parallel_copy(host + o, static_cast<const char*>(s->bounce[i & 1]), len);
+  }
+  return AB200_OK;
+}
+
 int ab200_get_columns(ab200_solver* s, int col0, int ncols, double* host, int64_t ld_host) {
   REQUIRE(s != nullptr && host != nullptr, "null argument");
   REQUIRE(col0 >= 0 && ncols >= 1 && col0 + ncols <= s->max_dim + 1, "column range [%d, %d) out of [0, %d]",
           col0, col0 + ncols, s->max_dim + 1);
   REQUIRE(ld_host >= s->n, "ld_host < nrows_local");
   CU(cudaSetDevice(s->device));
+  char* out = reinterpret_cast<char*>(host);
   if (s->real_mode) {
     // expand column by column through the scratch vector, lazy scale applied on the way out
     for (int c = 0; c < ncols; ++c) {
       CU(launch_unpack_real(static_cast<const double*>(col_ptr(s, col0 + c)), s->wtmp, s->n,
                             s->h_scale[col0 + c], s->num_sms, s->stream));
       s->st.kernel_launches += 1;
-      CU(cudaMemcpyAsync(host + 2 * (size_t)c * ld_host, s->wtmp, sizeof(cplx) * (size_t)s->n,
-                         cudaMemcpyDeviceToHost, s->stream));
+      int rc = download(s, out + sizeof(cplx) * (size_t)c * ld_host, reinterpret_cast<const char*>(s->wtmp),
+                        sizeof(cplx) * (size_t)s->n);
+      if (rc != AB200_OK) return rc;
     }
     CU(cudaStreamSynchronize(s->stream));
     return AB200_OK;
@@ -598,9 +732,12 @@ int ab200_get_columns(ab200_solver* s, int col0, int ncols, double* host, int64_
   // apply the lazy scales in place first (a no-op for columns whose scale is 1)
   CU(launch_materialize(s->V, s->n, s->ld, col0, ncols, s->scale, s->num_sms, s->stream));
   s->st.kernel_launches += 2;
-  CU(cudaMemcpy2DAsync(host, sizeof(cplx) * ld_host, s->V + (size_t)col0 * s->ld,
-                       sizeof(cplx) * s->ld, sizeof(cplx) * s->n, ncols, cudaMemcpyDeviceToHost,
-                       s->stream));
+  for (int c = 0; c < ncols; ++c) {
+    int rc = download(s, out + sizeof(cplx) * (size_t)c * ld_host,
+                      reinterpret_cast<const char*>(s->V + (size_t)(col0 + c) * s->ld),
+                      sizeof(cplx) * (size_t)s->n);
+    if (rc != AB200_OK) return rc;
+  }
   CU(cudaStreamSynchronize(s->stream));
   for (int i = 0; i < ncols; ++i) s->h_scale[col0 + i] = 1.0;
   return AB200_OK;
@@ -608,7 +745,20 @@ int ab200_get_columns(ab200_solver* s, int col0, int ncols, double* host, int64_
 
 static int enqueue_spmv(ab200_solver* s, const void* x, void* y, const double* xscale, int step,
                         bool in_expand) {
+  const bool real = in_expand && s->real_mode;
+  if (s->op_fn != nullptr) {
+    // device operator: hand it the true vector v_j = s_j U_j in a scratch buffer
+    const int64_t n16 = real ? (s->n + 1) / 2 : s->n;
+    LaunchScope ls(s, K_SPMV, step, 0, 0.0);
+    CU(launch_scaled_copy(static_cast<const cplx*>(x), s->xtmp, n16, xscale, real ? 1 : 0, s->num_sms,
+                          s->stream));
+    s->st.kernel_launches += 1;
+    const int rc = s->op_fn(s->op_user, s->xtmp, y, s->n, real ? 1 : 0, (void*)s->stream);
+    if (rc != 0) return set_err(AB200_ECUDA, "device operator callback returned %d", rc);
+    return AB200_OK;
+  }
   SpmvArgs a;
+  memset(&a, 0, sizeof(a));
   a.indptr = s->indptr;
   a.indices = s->indices;
   a.values = s->values;
@@ -622,11 +772,16 @@ static int enqueue_spmv(ab200_solver* s, const void* x, void* y, const double* x
   a.nblocks = s->nblk;
   a.tile = s->tile;
   a.threads = s->spmv_threads;
-  a.real = (in_expand && s->real_mode) ? 1 : 0;
-  a.long_rows = s->max_row_len > 16 ? 1 : 0;
+  a.real = real ? 1 : 0;
+  a.long_rows = (s->max_row_len > 16 || s->spmv_algo == AB200_SPMV_VECTOR ||
+                 s->spmv_algo == AB200_SPMV_MERGE) ? 1 : 0;
   a.variant = s->opt_spmv_variant;
   a.num_sms = s->num_sms;
   a.ctl = in_expand ? s->ctl : nullptr;
+  a.stages = s->spmv_stages;
+  a.rp_cap = s->spmv_rp_cap;
+  a.bps = s->opt_spmv_bps;
+  a.nranks = s->nranks;
   const double sv = s->value_kind == AB200_F64 ? 8.0 : 16.0;
   const double eb = a.real ? 8.0 : 16.0;
   const double bytes = (double)s->nnz * (sv + 4.0) + (double)s->n * (s->indptr_bits / 8 + 2.0 * eb) +
@@ -658,21 +813,37 @@ static int enqueue_spmv(ab200_solver* s, const void* x, void* y, const double* x
     s->st.kernel_launches += 2;
   } else if (s->nghost > 0) {
     if (!in_expand) return set_err(AB200_ESTATE, "halo SpMV is only available inside ab200_expand");
-    HaloArgs h;
-    for (int r = 0; r < kMaxRanks; ++r) {
-      h.peer_base[r] = r == s->rank ? s->V : static_cast<const cplx*>(s->peer_V[r]);
-      h.peer_ld[r] = s->peer_ld[r];
+    // "pull": the halo entries of column `step` are read from the owners' HBM.  Banded
+    // operators with short rows read them inside the SpMV itself (no extra launch, no ghost
+    // buffer round trip); otherwise a gather kernel fills the ghost buffer first.
+    const bool fold = s->opt_halo_fold && !a.long_rows && a.variant == 0;
+    const size_t col_bytes = (size_t)step * (a.real ? sizeof(double) : sizeof(cplx));
+    if (fold) {
+      a.direct_halo = 1;
+      a.ghost_off = s->ghost_off;
+      for (int r = 0; r < kMaxRanks; ++r) {
+        const char* base = r == s->rank ? reinterpret_cast<const char*>(s->V)
+                                        : static_cast<const char*>(s->peer_V[r]);
+        a.peer_col[r] = base ? base + col_bytes * (size_t)s->peer_ld[r] : nullptr;
+      }
+      for (int r = 0; r <= kMaxRanks; ++r) a.seg_start[r] = s->seg_start[r];
+    } else {
+      HaloArgs h;
+      for (int r = 0; r < kMaxRanks; ++r) {
+        h.peer_base[r] = r == s->rank ? s->V : static_cast<const cplx*>(s->peer_V[r]);
+        h.peer_ld[r] = s->peer_ld[r];
+      }
+      for (int r = 0; r <= kMaxRanks; ++r) h.seg_start[r] = s->seg_start[r];
+      h.src_off = s->ghost_off;
+      h.ghost = s->ghost;
+      h.nghost = s->nghost;
+      h.col = step;
+      h.real = a.real;
+      h.nranks = s->nranks;
+      h.ctl = s->ctl;
+      CU(launch_halo_gather(h, s->num_sms, s->stream));
+      s->st.kernel_launches += 1;
     }
-    for (int r = 0; r <= kMaxRanks; ++r) h.seg_start[r] = s->seg_start[r];
-    h.src_off = s->ghost_off;
-    h.ghost = s->ghost;
-    h.nghost = s->nghost;
-    h.col = step;
-    h.real = a.real;
-    h.nranks = s->nranks;
-    h.ctl = s->ctl;
-    CU(launch_halo_gather(h, s->num_sms, s->stream));
-    s->st.kernel_launches += 1;
   }
   CU(launch_spmv(a, s->indptr_bits, s->value_kind, s->stream));
   return AB200_OK;
@@ -687,7 +858,9 @@ int ab200_expand(ab200_solver* s, int start_dim, int end_dim, double tol, double
           s->max_dim);
   REQUIRE(ortho_kind == AB200_ORTHO_CGS2 || ortho_kind == AB200_ORTHO_MGS, "bad ortho_kind %d",
           ortho_kind);
-  if (s->nnz < 0) return set_err(AB200_ESTATE, "ab200_expand called before ab200_set_csr");
+  if (s->nnz < 0)
+    return set_err(AB200_ESTATE, "ab200_expand called before ab200_set_csr / ab200_set_operator");
+  if (s->disconnected) return set_err(AB200_ESTATE, "ab200_expand after ab200_comm_disconnect");
   CU(cudaSetDevice(s->device));
   s->pristine = false;
   const int md1 = s->max_dim + 1;
@@ -696,7 +869,7 @@ int ab200_expand(ab200_solver* s, int start_dim, int end_dim, double tol, double
   s->st.kernel_launches += 1;
   if (s->nranks > 1) {
     // every rank's basis (restart update / uploaded columns) is final before any halo read
-    CU(launch_peer_barrier(s->comm, s->ctl, s->stream));
+    CU(launch_peer_barrier(s->comm, s->ctl, s->real_mode ? 1 : 0, s->stream));
     s->st.kernel_launches += 1;
   }
   for (int j = start_dim; j < end_dim; ++j) {
@@ -721,6 +894,8 @@ int ab200_expand(ab200_solver* s, int start_dim, int end_dim, double tol, double
   CU(cudaMemcpyAsync(s->h_ctl, s->ctl, sizeof(StepCtl), cudaMemcpyDeviceToHost, s->stream));
   CU(cudaStreamSynchronize(s->stream));
   resolve_pending(s, s->h_step_round2);
+  if (s->h_ctl->comm_error == 2)
+    return set_err(AB200_ECOMM, "ranks disagree on real / complex storage of the basis");
   if (s->h_ctl->comm_error) return set_err(AB200_ECOMM, "peer reduction timed out");
   int done = end_dim;
   *breakdown = 0;
@@ -746,11 +921,9 @@ int ab200_expand(ab200_solver* s, int start_dim, int end_dim, double tol, double
   return AB200_OK;
 }
 
-int ab200_restart(ab200_solver* s, const double* q, int64_t ldq, int m, int p) {
-  REQUIRE(s != nullptr && q != nullptr, "null argument");
-  REQUIRE(m >= 1 && m <= s->max_dim && p >= 1 && p < m, "need 1 <= p (%d) < m (%d) <= max_dim (%d)", p,
-          m, s->max_dim);
-  REQUIRE(ldq >= m, "ldq < m");
+// shared by ab200_restart and ab200_combine: U[:, col0:col0+p] = U[:, col0:col0+m] q (+ tail)
+static int apply_q(ab200_solver* s, const double* q, int64_t ldq, int col0, int m, int p,
+                   bool copy_tail) {
   CU(cudaSetDevice(s->device));
   CU(cudaStreamSynchronize(s->stream));  // the pinned Q staging buffer is free again
   const cplx* qh = reinterpret_cast<const cplx*>(q);
@@ -762,7 +935,7 @@ int ab200_restart(ab200_solver* s, const double* q, int64_t ldq, int m, int p) {
           q_real = false;
           break;
         }
-    if (!q_real) {  // complex Schur vectors: the basis becomes complex from here on
+    if (!q_real) {  // complex coefficients: the basis becomes complex from here on
       int rc = switch_to_complex(s);
       if (rc != AB200_OK) return rc;
     }
@@ -771,29 +944,143 @@ int ab200_restart(ab200_solver* s, const double* q, int64_t ldq, int m, int p) {
   for (int i = 0; i < m; ++i)
     for (int k = 0; k < p; ++k) {
       const cplx v = qh[(size_t)k * ldq + i];
-      s->h_q[(size_t)i * p + k] = make_double2(v.x * s->h_scale[i], v.y * s->h_scale[i]);
+      const double sc = s->h_scale[col0 + i];
+      s->h_q[(size_t)i * p + k] = make_double2(v.x * sc, v.y * sc);
     }
   CU(cudaMemcpyAsync(s->qdev, s->h_q, sizeof(cplx) * (size_t)m * p, cudaMemcpyHostToDevice,
                      s->stream));
   RestartArgs a;
-  a.U = s->V;
+  a.copy_tail = copy_tail ? 1 : 0;
   a.real = s->real_mode ? 1 : 0;
+  a.U = static_cast<cplx*>(col_ptr(s, col0));
   a.n = s->real_mode ? (s->n + 1) / 2 : s->n;
   a.ld = s->real_mode ? s->ld / 2 : s->ld;
   a.m = m;
   a.p = p;
   a.q = s->qdev;
-  a.scale_m = s->h_scale[m];
+  a.scale_m = copy_tail ? s->h_scale[col0 + m] : 1.0;
   {
-    LaunchScope ls(s, K_RESTART, -1, 0, elem_bytes(s) * (double)s->n * (m + p + 2));
+    LaunchScope ls(s, K_RESTART, -1, 0, elem_bytes(s) * (double)s->n * (m + p + (copy_tail ? 2 : 0)));
     CU(launch_restart(a, s->num_sms, s->stream, s->opt_restart_variant));
   }
-  set_scale_kernel<<<1, 128, 0, s->stream>>>(s->scale, 0, p + 1, 1.0);
+  const int nreset = p + (copy_tail ? 1 : 0);
+  set_scale_kernel<<<1, 128, 0, s->stream>>>(s->scale, col0, nreset, 1.0);
   CU(cudaGetLastError());
   s->st.kernel_launches += 1;
   // no synchronisation here: the host goes on to update H and to enqueue the next expansion
   // while the update runs (the next call that reads results synchronises)
-  for (int i = 0; i <= p; ++i) s->h_scale[i] = 1.0;
+  for (int i = 0; i < nreset; ++i) s->h_scale[col0 + i] = 1.0;
+  s->pristine = false;
+  return AB200_OK;
+}
+
+int ab200_restart(ab200_solver* s, const double* q, int64_t ldq, int m, int p) {
+  REQUIRE(s != nullptr && q != nullptr, "null argument");
+  REQUIRE(m >= 1 && m <= s->max_dim && p >= 1 && p < m, "need 1 <= p (%d) < m (%d) <= max_dim (%d)", p,
+          m, s->max_dim);
+  REQUIRE(ldq >= m, "ldq < m");
+  return apply_q(s, q, ldq, 0, m, p, true);
+}
+
+// V[:, col0:col0+p] = V[:, col0:col0+m] q   (p <= m), nothing else touched: Ritz / Schur
+// vectors out of a block of basis columns (explicit_restarts.py:139,167; the last rotation of
+// a solve that ran in a real basis).
+int ab200_combine(ab200_solver* s, const double* q, int64_t ldq, int col0, int m, int p) {
+  REQUIRE(s != nullptr && q != nullptr, "null argument");
+  REQUIRE(col0 >= 0 && m >= 1 && p >= 1 && p <= m && col0 + m <= s->max_dim + 1,
+          "need col0 >= 0, 1 <= p (%d) <= m (%d), col0 + m <= max_dim + 1 (%d)", p, m, s->max_dim + 1);
+  REQUIRE(ldq >= m, "ldq < m");
+  return apply_q(s, q, ldq, col0, m, p, false);
+}
+
+// Orthonormalise basis column `col` against columns [0, ncols) on the device (ncols <= col):
+// CGS2/DGKS or MGS/DGKS as inside an expansion, then the column is normalised (lazily).
+// *beta is its norm after the projections; *breakdown = 1 when beta < tol (the column lies in
+// the span of the others and is left un-normalised).  Used to append a fresh direction after
+// a happy breakdown and for the deflation step of the explicit-restart solver
+// (explicit_restarts.py:63-77,111,141).
+int ab200_orthonormalize_column(ab200_solver* s, int col, int ncols, double tol, double eta,
+                                int ortho_kind, double* beta, int* breakdown) {
+  REQUIRE(s != nullptr && beta != nullptr && breakdown != nullptr, "null argument");
+  REQUIRE(col >= 0 && col <= s->max_dim && ncols >= 0 && ncols <= col && ncols <= s->max_dim,
+          "need 0 <= ncols (%d) <= col (%d) <= max_dim (%d)", ncols, col, s->max_dim);
+  REQUIRE(ortho_kind == AB200_ORTHO_CGS2 || ortho_kind == AB200_ORTHO_MGS, "bad ortho_kind %d",
+          ortho_kind);
+  if (s->disconnected)
+    return set_err(AB200_ESTATE, "ab200_orthonormalize_column after ab200_comm_disconnect");
+  CU(cudaSetDevice(s->device));
+  s->pristine = false;
+  init_ctl_kernel<<<1, 32, 0, s->stream>>>(s->ctl, nullptr, 0, false);
+  CU(cudaGetLastError());
+  CU(cudaMemsetAsync(s->hscratch, 0, sizeof(cplx) * (s->max_dim + 2), s->stream));
+  s->st.kernel_launches += 1;
+  cplx* w = static_cast<cplx*>(col_ptr(s, col));
+  if (ncols == 0) {
+    // nothing to project out: one norm pass (pass 2 with no columns) normalises the column
+    OrthoArgs a = make_ortho_args(s, w, 0, col - 1, tol, eta, s->hscratch, 2);
+    a.round = 2;  // no DGKS decision on a bare norm
+    CU(launch_cgs_pass2(a, s->num_sms, s->stream, s->opt_grid_mult));
+    s->st.kernel_launches += 1;
+  } else {
+    // hscratch plays column `col - 1` of H: finalize writes beta at row col and scale[col]
+    OrthoArgs a = make_ortho_args(s, w, ncols, col - 1, tol, eta, s->hscratch, 2);
+    const int saved = s->opt_ortho_variant;
+    s->opt_ortho_variant = 1;  // plain two-sweep rounds: the fused sweep assumes j == ncols - 1
+    int rc = enqueue_ortho(s, a, ortho_kind);
+    s->opt_ortho_variant = saved;
+    if (rc != AB200_OK) return rc;
+  }
+  CU(cudaMemcpyAsync(s->h_scale, s->scale, sizeof(double) * (s->max_dim + 1), cudaMemcpyDeviceToHost,
+                     s->stream));
+  CU(cudaMemcpyAsync(s->h_ctl, s->ctl, sizeof(StepCtl), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  {
+    int r2 = s->h_ctl->second_total > s->st.second_rounds ? 1 : 0;
+    std::vector<int> flags(s->max_dim + 1, r2);
+    resolve_pending(s, flags.data());
+  }
+  if (s->h_ctl->comm_error) return set_err(AB200_ECOMM, "peer reduction timed out");
+  *beta = s->h_ctl->beta;
+  *breakdown = s->h_ctl->stop ? 1 : 0;
+  s->st.arnoldi_steps = s->h_ctl->steps_total;
+  s->st.ortho_rounds = s->h_ctl->rounds_total;
+  s->st.second_rounds = s->h_ctl->second_total;
+  return AB200_OK;
+}
+
+// h[i] = <V_i, A V_col>, i < nrows: one SpMV into the scratch vector and one pass-1 sweep
+// (explicit_restarts.py:150-151).
+int ab200_project(ab200_solver* s, int col, int nrows, double* h_host) {
+  REQUIRE(s != nullptr && h_host != nullptr, "null argument");
+  REQUIRE(col >= 0 && col <= s->max_dim && nrows >= 1 && nrows <= s->max_dim + 1 && nrows <= kMaxDim,
+          "need 0 <= col (%d) <= max_dim and 1 <= nrows (%d) <= max_dim + 1", col, nrows);
+  if (s->nnz < 0) return set_err(AB200_ESTATE, "ab200_project called before an operator was set");
+  if (s->disconnected) return set_err(AB200_ESTATE, "ab200_project after ab200_comm_disconnect");
+  CU(cudaSetDevice(s->device));
+  init_ctl_kernel<<<1, 32, 0, s->stream>>>(s->ctl, nullptr, 0, false);
+  CU(cudaGetLastError());
+  s->st.kernel_launches += 1;
+  if (s->nranks > 1) {
+    CU(launch_peer_barrier(s->comm, s->ctl, s->real_mode ? 1 : 0, s->stream));
+    s->st.kernel_launches += 1;
+  }
+  CU(cudaMemsetAsync(s->hscratch, 0, sizeof(cplx) * (s->max_dim + 2), s->stream));
+  int rc = enqueue_spmv(s, col_ptr(s, col), s->wtmp, s->scale + col, col, true);
+  if (rc != AB200_OK) return rc;
+  // the scale vector has max_dim + 1 entries: pass 1 reads scale[i] for i < nrows <= max_dim + 1
+  OrthoArgs a = make_ortho_args(s, s->wtmp, nrows, nrows - 1, 0.0, 0.0, s->hscratch, 0);
+  a.round = 1;
+  a.accumulate = 0;
+  {
+    LaunchScope ls(s, K_PASS1, -1, 1, elem_bytes(s) * (double)s->n * (nrows + 1));
+    CU(launch_cgs_pass1(a, s->num_sms, s->stream, s->opt_grid_mult));
+  }
+  CU(cudaMemcpyAsync(s->h_H, s->hscratch, sizeof(cplx) * nrows, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaMemcpyAsync(s->h_ctl, s->ctl, sizeof(StepCtl), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  resolve_pending(s, nullptr);
+  if (s->h_ctl->comm_error) return set_err(AB200_ECOMM, "peer reduction timed out");
+  memcpy(h_host, s->h_H, sizeof(cplx) * nrows);
   return AB200_OK;
 }
 
@@ -824,6 +1111,7 @@ int ab200_ortho(ab200_solver* s, int ncols, double* w_host, double* h_host, doub
           s->max_dim);
   REQUIRE(ortho_kind == AB200_ORTHO_CGS2 || ortho_kind == AB200_ORTHO_MGS, "bad ortho_kind %d",
           ortho_kind);
+  if (s->disconnected) return set_err(AB200_ESTATE, "ab200_ortho after ab200_comm_disconnect");
   CU(cudaSetDevice(s->device));
   {  // the stand-alone plug takes an arbitrary complex w: work on complex storage
     int rc = switch_to_complex(s);
@@ -1104,6 +1392,12 @@ int ab200_set_option(ab200_solver* s, const char* key, int64_t value) {
     s->opt_ortho_variant = (int)value;
   else if (!strcmp(key, "spmv_variant"))
     s->opt_spmv_variant = (int)value;
+  else if (!strcmp(key, "spmv_stages"))
+    s->opt_spmv_stages = (int)value;
+  else if (!strcmp(key, "spmv_bps"))
+    s->opt_spmv_bps = (int)value;
+  else if (!strcmp(key, "halo_fold"))
+    s->opt_halo_fold = (int)value;
   else if (!strcmp(key, "fused_r"))
     s->opt_fused_r = (int)value;
   else if (!strcmp(key, "fused_stages"))

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define AB200_ABI_VERSION 1
+#define AB200_ABI_VERSION 2
 
 #define AB200_OK 0
 #define AB200_EINVAL (-1)  /* bad argument (maps to AssertionError in Python) */
@@ -47,10 +47,14 @@ extern "C" {
 #define AB200_ORTHO_MGS 1  /* dgks_mgs, ortho.py:9-53 */
 
 /* spmv_algo for ab200_set_csr */
-#define AB200_SPMV_AUTO 0
-#define AB200_SPMV_VECTOR 1 /* sub-warp (1..32 lanes) per row              */
-#define AB200_SPMV_STREAM 2 /* row blocks staged through shared memory     */
-#define AB200_SPMV_MERGE 3  /* merge-path split of rows+nnz for skewed rows */
+#define AB200_SPMV_AUTO 0   /* STREAM when no row has more than 16 entries, else MERGE         */
+#define AB200_SPMV_VECTOR 1 /* row-snapped nnz tiles; a warp sums every segment > 16 entries   */
+#define AB200_SPMV_STREAM 2 /* one thread per row, tiles moved by bulk copies (TMA) through a   \
+                               shared-memory ring; rows of <= 16 entries only (else EINVAL);    \
+                               bit-identical to scipy's csr_matvec                              */
+#define AB200_SPMV_MERGE 3  /* equal-nnz tiles cut INSIDE rows (merge-path), partial row sums   \
+                               fixed up in tile order; x window of banded operators staged in   \
+                               shared memory                                                    */
 
 typedef struct ab200_solver ab200_solver; /* opaque */
 
@@ -93,6 +97,17 @@ int ab200_destroy(ab200_solver *s);
 int ab200_set_csr(ab200_solver *s, const void *indptr, int indptr_bits, const int32_t *indices,
                   const void *values, int value_kind, int64_t nnz, int spmv_algo);
 
+/* A device operator instead of a CSR block (the duck-typed `A @ x` of decomposition.py:58 for
+ * operators without stored entries; README.md:119 "LinearOperator support").  Inside
+ * ab200_expand, step j calls fn(user, x, y, n, is_real, stream): x and y are DEVICE pointers to
+ * n entries (float64 when is_real, else interleaved complex128), x holds v_j; fn must ENQUEUE
+ * y = A x on the CUDA stream `stream` (a cudaStream_t) without synchronising, and return 0.
+ * value_kind says whether A is real (AB200_F64: the basis may stay in float64 storage) or
+ * complex.  Single GPU. */
+typedef int (*ab200_apply_fn)(void *user, const void *x, void *y, int64_t n, int is_real,
+                              void *stream);
+int ab200_set_operator(ab200_solver *s, ab200_apply_fn fn, void *user, int value_kind);
+
 /* Copy host complex128 columns into / out of V (column-major, leading dimension
  * ld_host in elements).  set_columns replaces `V[:, 0] = v0` (krylov_schur.py:46);
  * get_columns replaces the final `V[:, :nev]` view (krylov_schur.py:110). */
@@ -117,6 +132,23 @@ int ab200_expand(ab200_solver *s, int start_dim, int end_dim, double tol, double
  * V[:, :p] = V[:, :m] Q[:, :p];  V[:, p] = V[:, m].
  * q is host complex128, column-major m x p with leading dimension ldq. */
 int ab200_restart(ab200_solver *s, const double *q, int64_t ldq, int m, int p);
+
+/* V[:, col0:col0+p] = V[:, col0:col0+m] q  (p <= m; q host complex128 column-major m x p):
+ * Ritz / Schur vectors out of a block of basis columns, nothing else touched
+ * (explicit_restarts.py:139 `ritz.vectors[:, 0]`, :167 `V[:, :nev] @ Y`). */
+int ab200_combine(ab200_solver *s, const double *q, int64_t ldq, int col0, int m, int p);
+
+/* Orthonormalise basis column `col` against columns [0, ncols), ncols <= col, with the same
+ * kernels as an Arnoldi step; *beta = its norm after the projections, *breakdown = 1 when
+ * beta < tol (column left un-normalised).  The deflation `mgs(V[:, :k], v)` of
+ * explicit_restarts.py:63-77,111,141, and the fresh direction appended after a happy
+ * breakdown (krylov_schur.py:57-59 raises there). */
+int ab200_orthonormalize_column(ab200_solver *s, int col, int ncols, double tol, double eta,
+                                int ortho_kind, double *beta, int *breakdown);
+
+/* h[i] = <V[:, i], A V[:, col]> for i in [0, nrows)  (host complex128 out): the projection
+ * explicit_restarts.py:150-151 computes column by column with np.vdot. */
+int ab200_project(ab200_solver *s, int col, int nrows, double *h_host);
 
 /* ---- single-operation entry points (the plugs the reference exposes) ---- */
 
@@ -154,6 +186,10 @@ int ab200_comm_export(ab200_solver *s, void *blob);
 int ab200_comm_connect(ab200_solver *s, int rank, int nranks, const void *blobs,
                        const int64_t *row_starts);
 int ab200_set_halo(ab200_solver *s, const int64_t *ghost_cols, int64_t nghost);
+/* First half of the multi-GPU teardown: synchronise and unmap every peer buffer.  Every rank
+ * calls it, the ranks meet (host barrier), then each calls ab200_destroy -- so no rank frees
+ * memory a peer still maps or reads.  The handle accepts no further multi-GPU work. */
+int ab200_comm_disconnect(ab200_solver *s);
 /* Optional owner-side push of the halo (for scattered halos).  After ab200_set_halo on every
  * rank: ab200_halo_export writes a blob with the IPC handles of this rank's ghost buffer and
  * delivery flags; ab200_halo_connect takes all ranks' blobs plus, for every peer r, the LOCAL
@@ -185,10 +221,30 @@ int ab200_timer_stop(ab200_solver *s, double *elapsed_ms);
  *   "real_mode"       0 = keep the basis as complex128 from the start (default: float64
  *                     storage while A, v0 and every Q applied are real -- see DESIGN.md)
  *   "grid_mult"       resident blocks per SM for the orthogonalisation kernels
- *   "spmv_variant"    1 = plain tile kernel even when every row is short (default: streaming)
- *   "spmv_tile"       non-zeros staged per SpMV block    } take effect at the next
- *   "spmv_threads"    SpMV block size, 128 or 256        } ab200_set_csr */
+ *   "spmv_variant"    short rows: 0 = bulk-copy (TMA) pipeline, 1 = plain tile kernel,
+ *                     2 = cp.async streaming kernel (round 1)
+ *   "spmv_tile"       non-zeros staged per SpMV block    }
+ *   "spmv_threads"    SpMV block size, 128 or 256        } take effect at the next
+ *   "spmv_stages"     ring depth of the bulk pipeline    } ab200_set_csr
+ *   "spmv_bps"        resident SpMV blocks per SM (0 = what fits)
+ *   "halo_fold"       0 = separate halo gather kernel before each SpMV (default 1: banded
+ *                     operators read their halo inside the SpMV) */
 int ab200_set_option(ab200_solver *s, const char *key, int64_t value);
+
+/* ---- host side of a restart: the m x m "rotate" of krylov_schur.py:69-72 ----
+ * zgees on H_m, then the reference's ordered_schur: one ?trexc move per target slot in the
+ * order `perm` asks for (utils.py:52-63), then Q = Q1 Q2 -- the reference's LAPACK calls in
+ * the reference's order, issued from C so the GPUs wait as little as possible.  The library
+ * links no LAPACK: the caller passes the routine addresses (the Python driver takes them from
+ * scipy.linalg.cython_lapack, i.e. the very OpenBLAS the reference runs on).
+ *   phase 1  ab200_host_schur:  T1 (in place in `t`, column-major m x m), Q1 into `q`.
+ *   phase 2  ab200_host_reorder: given perm[m] = sort_function(diag(T1)), reorders T in place
+ *            and writes Q2 (the accumulated swaps, starting from the identity) into q; the
+ *            caller forms Q = Q1 Q2.
+ * work: caller-provided scratch of at least 4 m m + 8 m doubles. */
+int ab200_host_schur(void *zgees_fn, int m, double *t, double *q, double *work);
+int ab200_host_reorder(void *ztrexc_fn, int m, double *t, double *q, const int64_t *perm,
+                       double *work);
 
 /* Pinned host memory for callers that want asynchronous, full-speed uploads. */
 int ab200_host_alloc(void **out, int64_t bytes);

@@ -56,6 +56,31 @@ class FakeDeviceSolver:
     def restart(self, Q, m, p):
         oracle.restart_update(self.V, np.asarray(Q), m, p)
 
+    def combine(self, Q, col0, m, p):
+        Q = np.asarray(Q)[:m, :p]
+        self.V[:, col0:col0 + p] = self.V[:, col0:col0 + m] @ Q
+
+    def orthonormalize_column(self, col, ncols, tol, *, eta=np.sqrt(0.5), ortho=0):
+        fn = oracle.cgs_dgks if ortho == 0 else oracle.mgs_dgks
+        w = self.V[:, col]
+        h = np.zeros(max(ncols, 1), np.complex128)
+        if ncols:
+            beta, _ = fn(w, self.V[:, :ncols], h, tol, eta)
+        else:
+            beta = float(np.linalg.norm(w))
+        if beta >= tol:
+            w /= beta
+        return float(beta)
+
+    def project(self, col, nrows):
+        return self.V[:, :nrows].conj().T @ (self.A @ self.V[:, col])
+
+    def disconnect(self):
+        pass
+
+    def true_matvecs(self):
+        return self.counters.get("matvecs", 0)
+
     def stats(self):
         c = self.counters
         return {"arnoldi_steps": c.get("matvecs", 0), "ortho_rounds": c.get("rounds", 0),

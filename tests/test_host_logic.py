@@ -98,9 +98,38 @@ def test_operator_conversion():
     np.testing.assert_array_equal(sp.csr_matrix((d, ix, ip), shape=(20, 20)).toarray(), D)
     ip, ix, d, _ = as_csr(A.astype(np.float32))
     assert d.dtype == np.float64
-    from scipy.sparse.linalg import aslinearoperator
+    # wrappers that expose the wrapped matrix as `.A` are unwrapped (scripts/utils.py:55-68 of
+    # the reference wraps A in MatvecCounter(LinearOperator) before calling partial_schur)
+    from scipy.sparse.linalg import LinearOperator, aslinearoperator
+    from arnoldi_b200.operator import credit_matvecs, unwrap
+    ip, ix, d, shape = as_csr(aslinearoperator(A))
+    assert ip is A.indptr and d is A.data and shape == (20, 20)
+
+    class MatvecCounter(LinearOperator):          # the reference's class, with a working base init
+        def __init__(self, A):
+            super().__init__(np.dtype(A.dtype), A.shape)
+            self.A = A
+            self.matvecs = 0
+
+        def _matvec(self, x):
+            self.matvecs += 1
+            return self.A @ x
+
+    class BareCounter:                            # scripts/utils.py:55-60 verbatim shape: no base init
+        def __init__(self, A):
+            self.A, self.shape, self.dtype, self.matvecs = A, A.shape, np.dtype(A.dtype), 0
+
+    for W in (MatvecCounter, BareCounter):
+        outer = W(W(A))
+        M, wrappers = unwrap(outer)
+        assert M is A and len(wrappers) == 2
+        credit_matvecs(wrappers, 37)
+        assert outer.matvecs == 37 and outer.A.matvecs == 37
+        assert as_csr(outer)[2] is A.data
+    # an opaque callable has no entries to upload: loud TypeError, never a host fallback
+    opaque = LinearOperator((20, 20), matvec=lambda x: A @ x, dtype=np.float64)
     with pytest.raises(TypeError, match="LinearOperator"):
-        as_csr(aslinearoperator(A))
+        as_csr(opaque)
 
 
 def test_history_and_argument_checks():
