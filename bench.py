@@ -10,7 +10,7 @@ sort = largest real part, tol = 1e-8, v0 = ``np.random.seed(0); randn(n)`` norma
 A *step* is one Krylov-Schur restart cycle of that solve at full size: host Schur +
 reorder of H (40 x 40), the in-place truncation V[:, :15] = V Q, and the Arnoldi
 expansion from column 15 to 40 (25 SpMV + 25 CGS2/DGKS orthogonalisations).  The full
-solve needs on the order of 10^3 such cycles at this size, far
+solve needs on the order of 10^4 such cycles at this size, far
 beyond a benchmark run and far beyond what the CPU reference can finish, so the
 headline is the cycle throughput in Arnoldi matvecs per second:
 
@@ -19,24 +19,43 @@ headline is the cycle throughput in Arnoldi matvecs per second:
          CSR + v0 uploaded from pinned host memory and Q, T read back inside the timing
   roofline       the kernel class with the largest share of the step, algorithmic bytes
                   / CUDA-event time, against MEASURED_PEAKS.json
-  cpu_baseline   the oracle (a restatement of the reference calling the same SciPy /
-                 OpenBLAS routines) on the host cores, same operator family at reduced n
+  cpu_baseline   the UNMODIFIED reference (baseline/_ref, installed by
+                 tools/install_reference.py) on the host cores, same operator, same size:
+                 Arnoldi steps 15..39 of its first expansion (the column counts of one
+                 restart cycle), timed at the operator
+  converged      BASELINE.json's own metric, time-to-k-converged, on an instance both arms
+                 can finish: mark(400) (n = 80 200, nonsymmetric), K = 20, max_dim = 60
+  parity         seeded solves against the reference's records (tests/golden) run before
+                 the timing, at whatever rank count the benchmark runs on
 
-``--impl reference`` times that CPU path alone, in the same unit.
+``--impl reference`` times the reference alone on the same operator at the same size: its own
+``partial_schur`` is run on a time-stamping operator; the timed region is whole restart cycles
+(boundaries = the first operator application of each expansion).  A cycle costs ~25 s on the
+box's host cores, so the timed region is ``--ref-cycles`` cycles (default 2) whatever K is, and
+``ms_per_step`` is that region divided by K: a bounded sample of the workload, as measured.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
-import subprocess
 import sys
-import threading
-import time
-
-import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+_REFERENCE_ARM = "reference" in sys.argv[1:] and "--impl" in sys.argv[1:]
+if _REFERENCE_ARM or os.environ.get("AB200_BENCH_CPU_THREADS"):
+    # torchrun exports OMP_NUM_THREADS=1 to its children: the CPU arm would silently run its
+    # BLAS on one core.  The thread count of the CPU arm is set explicitly, before NumPy loads.
+    _n = os.environ.get("AB200_BENCH_CPU_THREADS") or str(os.cpu_count() or 1)
+    for _k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_k] = _n
+
+import subprocess  # noqa: E402
+import threading  # noqa: E402
+import time  # noqa: E402
+
+import numpy as np  # noqa: E402
+
 for _p in (ROOT, os.path.join(ROOT, "arnoldi-py_b200")):
     if _p not in sys.path:
         sys.path.insert(0, _p)
@@ -44,9 +63,9 @@ for _p in (ROOT, os.path.join(ROOT, "arnoldi-py_b200")):
 NEV, MAX_DIM, TOL = 10, 40, 1e-8
 P = min(NEV + 5, MAX_DIM - 1)
 GRID_FULL = 4096          # config 2
-GRID_CPU = 1024           # CPU sample: same operator family, n = 1 048 576
 METRIC = "partial_schur Arnoldi matvecs/s (restart cycles, config 2)"
 UNIT = "matvec/s"
+CONV = dict(m=400, nev=20, max_dim=60)      # the converged leg: mark(400)
 
 
 # ----------------------------------------------------------------------------- helpers
@@ -113,13 +132,16 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def host_threads():
+def set_host_threads():
+    """All host cores for the CPU arm, whatever the launcher exported; returns the count
+    OpenBLAS actually uses."""
+    want = int(os.environ.get("AB200_BENCH_CPU_THREADS") or os.cpu_count() or 1)
     try:
-        from threadpoolctl import threadpool_info
-        n = max((d.get("num_threads", 1) for d in threadpool_info()), default=1)
-        return int(n)
+        from threadpoolctl import threadpool_info, threadpool_limits
+        threadpool_limits(limits=want)
+        return int(max((d.get("num_threads", 1) for d in threadpool_info()), default=1))
     except Exception:
-        return os.cpu_count() or 1
+        return want
 
 
 def pinned_csr(dev_lib, A):
@@ -146,76 +168,141 @@ def pinned_csr(dev_lib, A):
 
 
 # ----------------------------------------------------------------------------- CPU arm
-def cpu_cycles(steps, warmup, grid=GRID_CPU):
-    """Reference CPU path: restart cycles of the same solve on lap2d(grid), timed with
-    perf_counter around each cycle (scripts/utils.py:161-174 of the reference)."""
+def load_cpu_arm():
+    """The CPU implementation to time: the unmodified reference installed under baseline/_ref
+    (kind "reference"), else the oracle's restatement of it (kind "port")."""
+    import importlib.util
+    init = os.path.join(ROOT, "baseline", "_ref", "arnoldi", "__init__.py")
+    if os.path.exists(init):
+        spec = importlib.util.spec_from_file_location(
+            "arnoldi_reference", init, submodule_search_locations=[os.path.dirname(init)])
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules["arnoldi_reference"] = mod
+        spec.loader.exec_module(mod)
+        import arnoldi_reference.utils as ru
+        return dict(kind="reference", partial_schur=mod.partial_schur,
+                    sort=ru.arg_largest_real,
+                    what="unmodified cournape/arnoldi-py partial_schur (baseline/_ref)")
     import oracle
-    from arnoldi_b200.matrices import lap2d
-    from scipy.linalg import schur
+    return dict(kind="port", partial_schur=oracle.partial_schur, sort=oracle.arg_largest_real,
+                what="oracle/krylov.py (restatement of the reference: baseline/_ref is absent)")
 
-    A = lap2d(grid)
-    n = A.shape[0]
+
+class _Enough(Exception):
+    pass
+
+
+class StampedOperator:
+    """Duck-typed operator (shape, dtype, @ -- all the reference uses, decomposition.py:44,58)
+    that records the wall clock at every application and stops the solve after `limit`."""
+
+    def __init__(self, A, limit):
+        self.A = A
+        self.shape = A.shape
+        self.dtype = A.dtype
+        self.limit = limit
+        self.stamps = []
+
+    def __matmul__(self, x):
+        self.stamps.append(time.perf_counter())
+        if len(self.stamps) > self.limit:
+            raise _Enough()
+        return self.A @ x
+
+
+def cpu_partial_cycles(arm, A, cycles):
+    """Run the CPU arm's partial_schur on config 2 and time `cycles` restart cycles
+    (cycles = 0: only steps 15..39 of the first expansion).  Returns (matvecs, seconds, note)."""
+    first = MAX_DIM
+    per = MAX_DIM - P
+    limit = first + cycles * per if cycles > 0 else first
+    op = StampedOperator(A, limit)
     np.random.seed(0)
-    V = np.zeros((n, MAX_DIM + 1), np.complex128, order="F")
-    H = np.zeros((MAX_DIM + 1, MAX_DIM), np.complex128)
-    V[:, 0] = oracle.rand_unit_vector(n, np.complex128)
-    t_first = time.perf_counter()
-    oracle.arnoldi_expand(A, V, H, TOL, start_dim=0, max_dim=MAX_DIM)
-    t_first = time.perf_counter() - t_first
-
-    def cycle():
-        m = MAX_DIM
-        T1, Q1 = schur(H[:m, :m], output="complex")
-        T2, Q2 = oracle.sorted_schur(T1, oracle.arg_largest_real)
-        Q = Q1 @ Q2
-        spike = H[m, :m] @ Q[:, :P]
-        oracle.restart_update(V, Q, m, P)
-        H[:P, :P] = T2[:P, :P]
-        H[P, :P] = spike
-        H[P, P:] = 0
-        oracle.arnoldi_expand(A, V, H, TOL, start_dim=P, max_dim=m)
-
-    for _ in range(warmup):
-        cycle()
     t0 = time.perf_counter()
-    for _ in range(steps):
-        cycle()
+    try:
+        arm["partial_schur"](op, NEV, max_dim=MAX_DIM, stopping_criterion=TOL,
+                             sort_function=arm["sort"], max_restarts=cycles + 2)
+        raise RuntimeError("the CPU solve ended before the sample was complete")
+    except _Enough:
+        pass
+    total = time.perf_counter() - t0
+    st = op.stamps
+    if cycles > 0:
+        # cycle i = [first application of expansion i, first application of expansion i + 1):
+        # 25 operator applications + orthogonalisations, then Schur / reorder / restart GEMM
+        seconds = st[first + cycles * per] - st[first]
+        matvecs = cycles * per
+        note = (f"{cycles} whole restart cycles ({matvecs} matvecs) of {arm['what']} on config 2 at "
+                f"full size, after its first expansion ({first} matvecs) as warm-up; cycle "
+                "boundaries are the first operator application of each expansion")
+    else:
+        # steps j = P .. MAX_DIM-1 of the first expansion have the column counts of a cycle; the
+        # sample runs from the operator application of step P to the first application after
+        # the first restart, so it also holds one Schur + reorder + restart GEMM: one cycle's work
+        seconds = st[first] - st[P]
+        matvecs = per
+        note = (f"Arnoldi steps {P}..{first - 1} of the first expansion plus the first restart "
+                f"(Schur, reorder, V[:, :p] = V Q) = the work of one restart cycle, {matvecs} "
+                f"matvecs, of {arm['what']} on config 2 at full size")
+    return matvecs, seconds, note, total
+
+
+def cpu_converged(arm):
+    """Time-to-k-converged of the CPU arm on the converged-leg instance (scripts/utils.py:161-174:
+    perf_counter around the call)."""
+    from arnoldi_b200.matrices import mark
+    A = mark(CONV["m"])
+    np.random.seed(0)
+    t0 = time.perf_counter()
+    Q, T, hist = arm["partial_schur"](A, CONV["nev"], max_dim=CONV["max_dim"],
+                                      stopping_criterion=TOL, sort_function=arm["sort"],
+                                      max_restarts=5000)
     dt = time.perf_counter() - t0
-    return dict(n=n, seconds=dt, matvecs=steps * (MAX_DIM - P), first_expansion_s=t_first)
+    return dict(time_to_k_converged_s=dt, restarts=int(hist.restarts[0]),
+                diagT=np.array(np.diag(T)))
 
 
-def cpu_baseline_dict(steps, warmup):
-    r = cpu_cycles(steps, warmup)
-    full_n = GRID_FULL * GRID_FULL
-    rate_sample = r["matvecs"] / r["seconds"]
-    value = rate_sample * r["n"] / full_n   # per-matvec cost is linear in n (bandwidth-bound)
-    return {
-        "value": value, "unit": UNIT, "cores": host_threads(), "kind": "port",
-        "sample": (f"{steps} restart cycles ({r['matvecs']} matvecs, {r['seconds']:.1f} s) of the "
-                   f"same solve on lap2d({GRID_CPU}) n={r['n']}; measured {rate_sample:.2f} "
-                   f"matvec/s there, scaled by n_sample/n_full = 1/{full_n // r['n']} to config 2; "
-                   "oracle = restatement of the reference calling the same scipy csr_matvec "
-                   "(1 thread) / OpenBLAS zgemv, zgemm (all threads)"),
-        "os_cpu_count": os.cpu_count(),
-    }
+def conv_workload():
+    m = CONV["m"]
+    return (f"mark({m}) n={m * (m + 1) // 2} (BASELINE config 3 family), K={CONV['nev']}, "
+            f"max_dim={CONV['max_dim']}, LR, tol={TOL}, seed 0, to convergence")
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from arnoldi_b200.matrices import lap2d
+    threads = set_host_threads()
+    arm = load_cpu_arm()
     steps = max(1, args.steps)
-    base = cpu_baseline_dict(steps, max(0, min(args.warmup, 3)))
+    cycles = max(1, min(steps, args.ref_cycles))
+    A = lap2d(args.grid)
+    matvecs, seconds, note, total = cpu_partial_cycles(arm, A, cycles)
+    value = matvecs / seconds
+    conv = None
+    if not args.no_converged:
+        c = cpu_converged(arm)
+        conv = {"workload": conv_workload(), "time_to_k_converged_s": c["time_to_k_converged_s"],
+                "restarts": c["restarts"], "ritz_real_top3": [float(x) for x in c["diagT"].real[:3]]}
+    base = {"value": value, "unit": UNIT, "cores": threads, "kind": arm["kind"],
+            "sample": note + f"; {seconds:.1f} s timed of {total:.1f} s run; csr_matvec is "
+                             "single-threaded, OpenBLAS uses all threads",
+            "os_cpu_count": os.cpu_count()}
     line = {
-        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT,
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
         "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * (MAX_DIM - P) / base["value"],
+        "ms_per_step": 1e3 * seconds / steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "c128",
         "data": "synthetic",
-        "config": workload_config(),
+        "config": workload_config(args.grid),
+        "timed_cycles": cycles, "timed_matvecs": matvecs, "timed_region_s": seconds,
+        "step_note": (f"timed region = {cycles} restart cycles; ms_per_step = timed region / "
+                      f"{steps} (a bounded sample: one reference cycle costs "
+                      f"{seconds / cycles:.1f} s)"),
         "cpu_baseline": base,
-        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
-                "d2h_bytes_per_step": 0},
+        "converged": conv,
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
 
@@ -227,23 +314,129 @@ def storage_note(st):
             if st.get("real_storage") else "c128")
 
 
-def workload_config():
+def workload_config(grid=GRID_FULL):
+    if grid != GRID_FULL:
+        return {"workload": f"lap2d({grid}) REDUCED (not config 2)"}
     return {"workload": f"lap2d({GRID_FULL}) n={GRID_FULL**2} nnz={5*GRID_FULL**2-4*GRID_FULL} "
                         f"float64 CSR, K={NEV}, max_dim={MAX_DIM}, p={P}, LR, tol={TOL}, seed 0",
             "step": f"one Krylov-Schur restart cycle: Schur+reorder (host, {MAX_DIM}x{MAX_DIM}), "
                     f"truncation V[:, :{P}] = V Q, expansion {P}->{MAX_DIM} "
                     f"({MAX_DIM-P} SpMV + CGS2/DGKS)",
-            "l2": "inputs larger than L2 (V = 11.0 GB, A = 1.07 GB)"}
+            "l2": "inputs larger than L2 (V = 11.0 GB, A = 1.07 GB)",
+            "ritz_parity_note": "this operator has double eigenvalues: its Ritz-value parity is "
+                                "pinned at N <= 64 and by eigenvalue membership + residual beyond; "
+                                "the `parity` block is on operators with simple spectra"}
+
+
+# ----------------------------------------------------------------------------- parity
+def parity_block(comm=None, device=0):
+    """Seeded solves against the reference's records (tests/golden), through the public API at
+    the rank count of this run.  Returns a JSON-able dict (`ok` per case, `all_ok`)."""
+    import scipy.sparse as sp
+
+    from arnoldi_b200 import partial_schur
+    from arnoldi_b200.matrices import mark
+    from arnoldi_b200.utils import arg_largest_real
+    g1 = np.load(os.path.join(ROOT, "tests", "golden", "solves.npz"))
+    g2 = np.load(os.path.join(ROOT, "tests", "golden", "solves_r2.npz"))
+
+    def rect(N):
+        return sp.csr_matrix((g2[f"rect{N}_data"], g2[f"rect{N}_indices"], g2[f"rect{N}_indptr"]),
+                             shape=tuple(int(x) for x in g2[f"rect{N}_shape"]))
+
+    cases = [("mark50_s0", g1, mark(50), 5, 20), ("mark100_s0", g1, mark(100), 20, 60),
+             ("rect64_s0", g2, rect(64), 10, 40)]
+    out = {}
+    for tag, g, A, nev, md in cases:
+        np.random.seed(0)
+        Q, T, hist = partial_schur(A, nev, max_dim=md, stopping_criterion=TOL, max_restarts=2000,
+                                   sort_function=arg_largest_real, device=device, comm=comm)
+        if comm is not None and comm.world > 1:
+            pieces = comm.all_gather_bytes(np.ascontiguousarray(Q).tobytes())
+            Q = np.concatenate([np.frombuffer(b, np.complex128).reshape(-1, nev) for b in pieces])
+        lam, ref = np.diag(T), g[f"{tag}_diagT"]
+        rel = np.abs(lam - ref) / np.abs(ref)
+        res = np.linalg.norm(A @ Q - Q @ T, axis=0)
+        R, Rref = int(hist.restarts[0]), int(g[f"{tag}_hist_restarts"][0])
+        ok = bool(R == Rref and np.sum(rel > 1e-10) <= max(1, nev // 10) and rel.max() < 1e-8
+                  and res.max() < 1e-7)
+        out[tag] = {"R": R, "R_ref": Rref, "max_rel": float(rel.max()),
+                    "n_above_1e-10": int(np.sum(rel > 1e-10)), "max_residual": float(res.max()),
+                    "ok": ok}
+    out["all_ok"] = all(v["ok"] for v in out.values())
+    out["rule"] = ("identical restart counts; Ritz values 1e-10 relative except the last-converged "
+                   "pair(s) (<= max(1, K//10) of them, < 1e-8: determined only to their residual, "
+                   "SURVEY.md section 8c); Schur residual < 1e-7")
+    return out
+
+
+def converged_leg(cpu, comm=None, device=0):
+    """BASELINE.json's metric on an instance both arms finish: our partial_schur from host CSR,
+    wall clock around the call, in the default (reference-faithful) and the real-arithmetic mode."""
+    from arnoldi_b200 import partial_schur
+    from arnoldi_b200.matrices import mark
+    from arnoldi_b200.utils import arg_largest_real
+    A = mark(CONV["m"])
+    out = {"workload": conv_workload()}
+    for mode in ("lossless", "pairs"):
+        best = None
+        for rep in range(2):            # rep 0 warms the CUDA context / allocator
+            np.random.seed(0)
+            stats = {}
+            if comm is not None:
+                comm.barrier()
+            t0 = time.perf_counter()
+            Q, T, hist = partial_schur(A, CONV["nev"], max_dim=CONV["max_dim"],
+                                       stopping_criterion=TOL, sort_function=arg_largest_real,
+                                       max_restarts=5000, stats=stats, device=device, comm=comm,
+                                       real_arith=mode)
+            dt = time.perf_counter() - t0
+            if comm is not None:
+                dt = comm.max_float(dt)
+            best = dt if best is None or rep > 0 else best
+        ent = {"time_to_k_converged_s": best, "restarts": int(hist.restarts[0]),
+               "matvecs": int(stats["true_matvecs"]), "real_storage_at_end": int(stats["real_storage"])}
+        if cpu is not None:
+            ref = cpu["diagT"]
+            lam = np.diag(T)
+            a, b = np.sort_complex(lam), np.sort_complex(ref)
+            rel = np.abs(a - b) / np.abs(b)
+            ent["max_rel_ritz_diff_vs_cpu"] = float(rel.max())
+            ent["ritz_above_1e-10"] = int(np.sum(rel > 1e-10))
+        out["b200_" + mode] = ent
+    if cpu is not None:
+        out["cpu"] = {"time_to_k_converged_s": cpu["time_to_k_converged_s"],
+                      "restarts": cpu["restarts"]}
+        out["speedup_lossless"] = cpu["time_to_k_converged_s"] / out["b200_lossless"]["time_to_k_converged_s"]
+        out["speedup_pairs"] = cpu["time_to_k_converged_s"] / out["b200_pairs"]["time_to_k_converged_s"]
+    out["note"] = ("lossless = the reference's iteration (restart counts identical up to summation "
+                   "order); pairs = real arithmetic with conjugate pairs kept whole, a different "
+                   "truncation, so its restart count is stated, not equal")
+    return out
 
 
 # ----------------------------------------------------------------------------- GPU arm
-def run_b200(args):
-    from scipy.linalg import schur
+def kernel_table(st, ms, peak):
+    classes = {}
+    for key in ("spmv", "ortho_pass1", "ortho_fused", "ortho_pass2", "restart"):
+        if st[key + "_launches"] and st[key + "_ms"] > 0:
+            classes[key] = dict(ms=st[key + "_ms"], bytes=st[key + "_bytes"],
+                                launches=st[key + "_launches"],
+                                gbs=st[key + "_bytes"] / st[key + "_ms"] / 1e6)
+    top = max(classes, key=lambda k: classes[k]["ms"])
+    kernels = {k: {"launches": v["launches"], "avg_ms": v["ms"] / v["launches"],
+                   "achieved_gbs": v["gbs"], "frac_of_measured": v["gbs"] / peak,
+                   "frac_of_8tbs": v["gbs"] / 8000.0,
+                   "share_of_step": v["ms"] / ms} for k, v in classes.items()}
+    return classes, top, kernels
 
+
+def run_b200(args):
     from arnoldi_b200 import _lib, partial_schur
     from arnoldi_b200.matrices import lap2d
+    from arnoldi_b200.rotate import rotate
     from arnoldi_b200.solver import DeviceSolver
-    from arnoldi_b200.utils import arg_largest_real, ordered_schur, rand_normalized_vector
+    from arnoldi_b200.utils import arg_largest_real, rand_normalized_vector
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -254,6 +447,7 @@ def run_b200(args):
     lib = _lib.load()
     if lib.ab200_device_count() < 1:
         raise SystemExit("bench.py: no CUDA device -- the B200 arm has no CPU fallback")
+    parity = None if args.no_parity else parity_block(device=local)
     grid = args.grid
     A = lap2d(grid)
     n = A.shape[0]
@@ -264,9 +458,13 @@ def run_b200(args):
     dev = DeviceSolver(n, MAX_DIM, device=local)
     if args.complex_storage:
         dev.set_option("real_mode", 0)
+    for kv in args.option:
+        k, v = kv.split("=")
+        dev.set_option(k, int(v))
     dev.set_timing(True)
     dev.set_csr(A.indptr, A.indices, A.data)
     dev.set_columns(0, v0)
+    host_ms = []
 
     def grow(start):
         cols, n_iter, brk = dev.expand(start, MAX_DIM, TOL)
@@ -276,10 +474,10 @@ def run_b200(args):
 
     def cycle():
         m = MAX_DIM
-        T1, Q1 = schur(H[:m, :m], output="complex")
-        T2, Q2 = ordered_schur(T1, output="complex", sort_function=arg_largest_real)
-        Q = Q1 @ Q2
+        t0 = time.perf_counter()
+        T2, Q = rotate(H[:m, :m], arg_largest_real)
         spike = H[m, :m] @ Q[:, :P]
+        host_ms.append(1e3 * (time.perf_counter() - t0))
         dev.restart(Q, m, P)
         H[:P, :P] = T2[:P, :P]
         H[P, :P] = spike
@@ -291,6 +489,7 @@ def run_b200(args):
         cycle()
     dev.synchronize()
     dev.reset_stats()
+    host_ms.clear()
     clocks = ClockSampler(local)
     clocks.start()
     dev.timer_start()
@@ -307,22 +506,14 @@ def run_b200(args):
 
     # ---- roofline of the dominant kernel class (CUDA events inside the timed region)
     peak, peak_src = measured_peak()
-    classes = {}
-    for key in ("spmv", "ortho_pass1", "ortho_fused", "ortho_pass2", "restart"):
-        if st[key + "_launches"]:
-            classes[key] = dict(ms=st[key + "_ms"], bytes=st[key + "_bytes"],
-                                launches=st[key + "_launches"],
-                                gbs=st[key + "_bytes"] / st[key + "_ms"] / 1e6)
-    top = max(classes, key=lambda k: classes[k]["ms"])
-    kernels = {k: {"launches": v["launches"], "avg_ms": v["ms"] / v["launches"],
-                   "achieved_gbs": v["gbs"], "frac_of_measured": v["gbs"] / peak,
-                   "frac_of_8tbs": v["gbs"] / 8000.0,
-                   "share_of_step": v["ms"] / ms} for k, v in classes.items()}
+    classes, top, kernels = kernel_table(st, ms, peak)
     roofline = {"bound": "hbm", "kernel": top, "achieved": classes[top]["gbs"], "peak": peak,
                 "unit": "GB/s", "frac": classes[top]["gbs"] / peak, "peak_source": peak_src,
-                "traffic": traffic_from_profile(top, grid, classes[top]["bytes"] / classes[top]["launches"]),
+                "traffic": traffic_from_profile(top, grid, st, classes[top]["bytes"] / classes[top]["launches"]),
                 "algorithmic_bytes_per_launch": classes[top]["bytes"] / classes[top]["launches"],
                 "kernels": kernels,
+                "kernel_sum_ms_per_step": sum(v["ms"] for v in classes.values()) / args.steps,
+                "host_rotate_ms_per_step": float(np.mean(host_ms)),
                 "dgks_second_round_fraction": st["second_rounds"] / max(1, st["arnoldi_steps"])}
     dev.close()
 
@@ -352,36 +543,51 @@ def run_b200(args):
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "call": f"partial_schur(A_host, {NEV}, max_dim={MAX_DIM}, max_restarts={restarts}) "
                        f"= {mv} matvecs per call, {float(np.mean(times)):.3f} s per call incl. "
-                       "v0 = randn(n) on the host, CSR upload from pinned memory, Q/T download",
+                       "v0 = randn(n) on the host, CSR upload from pinned memory, Q/T download; "
+                       "bytes are per CALL (one upload of A and v0, one download of Q and T)",
                "reps": len(times),
                "host_phases_s": {k: round(v, 4) for k, v in out.get("host_phases_s", {}).items()}}
         for ptr in keep:
             lib.ab200_host_free(ptr)
 
-    cpu = None if args.no_cpu else cpu_baseline_dict(args.cpu_steps, 1)
+    cpu = None
+    cpu_conv = None
+    if not args.no_cpu:
+        threads = set_host_threads()
+        arm = load_cpu_arm()
+        matv, secs, note, total = cpu_partial_cycles(arm, A, 0)
+        cpu = {"value": matv / secs, "unit": UNIT, "cores": threads, "kind": arm["kind"],
+               "sample": note + f"; {secs:.1f} s timed of {total:.1f} s run; csr_matvec is "
+                                "single-threaded, OpenBLAS uses all threads",
+               "os_cpu_count": os.cpu_count()}
+        if not args.no_converged:
+            cpu_conv = cpu_converged(arm)
+    del A
+    converged = None if args.no_converged else converged_leg(cpu_conv, device=local)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": storage_note(st), "data": "synthetic",
-        "config": workload_config() if grid == GRID_FULL else
-        {"workload": f"lap2d({grid}) REDUCED (not config 2)"},
+        "config": workload_config(grid),
         "wall_ms_per_step": 1e3 * wall / args.steps,
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "converged": converged,
+        "parity": parity,
         "gpu_launches": int(st["kernel_launches"]), "clocks": clk,
     }
     print(json.dumps(line))
 
 
-def traffic_from_profile(kernel, grid, bytes_per_launch=None):
+def traffic_from_profile(kernel, grid, st, bytes_per_launch=None):
     """DRAM bytes per launch of the dominant kernel, from the committed `ncu --set full`
-    capture (profiles/traffic.json: measured DRAM bytes / algorithmic bytes of one launch)
-    scaled to the average launch of this run; None when no capture covers the kernel."""
+    capture (profiles/traffic.json: measured DRAM bytes / algorithmic bytes of one launch, per
+    storage mode) scaled to the average launch of this run; None when no capture covers it."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             t = json.load(f)
-        ent = t.get(f"{kernel}@lap2d({grid})")
+        mode = "real" if st.get("real_storage") else "complex"
+        ent = t.get(f"{kernel}@lap2d({grid})@{mode}") or t.get(f"{kernel}@lap2d({grid})")
         if ent is None or bytes_per_launch is None:
             return None
         return float(ent["ratio"]) * float(bytes_per_launch)
@@ -391,24 +597,24 @@ def traffic_from_profile(kernel, grid, bytes_per_launch=None):
 
 def run_b200_multi(args, rank, world, local):
     """Strong scaling on one box: the SAME config-2 solve, rows of A and V block-row
-    sharded over `world` GPUs (one process each); halo of v pulled from peer HBM over
-    NVLink inside the SpMV's gather kernel, inner products combined inside the reducing
-    kernels over peer memory.  torch.distributed (NCCL) only bootstraps and takes the max
-    of the per-rank timings."""
+    sharded over `world` GPUs (one process each); halo of v read from peer HBM over
+    NVLink inside the SpMV, inner products combined inside the reducing kernels over peer
+    memory.  torch.distributed (NCCL) only bootstraps and takes the max of the per-rank
+    timings."""
     import torch
     import torch.distributed as dist
-    from scipy.linalg import schur
 
-    from arnoldi_b200 import _lib, partial_schur
+    from arnoldi_b200 import partial_schur
     from arnoldi_b200.distributed import RowPartition, TorchComm, build_halo_plan, slice_rows
     from arnoldi_b200.matrices import lap2d
+    from arnoldi_b200.rotate import rotate
     from arnoldi_b200.solver import DeviceSolver
-    from arnoldi_b200.utils import arg_largest_real, ordered_schur, rand_normalized_vector
+    from arnoldi_b200.utils import arg_largest_real, rand_normalized_vector
 
-    os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     comm = TorchComm()
+    parity = None if args.no_parity else parity_block(comm=comm, device=local)
     grid = args.grid
     A = lap2d(grid)
     n = A.shape[0]
@@ -422,11 +628,15 @@ def run_b200_multi(args, rank, world, local):
     dev = DeviceSolver(n, MAX_DIM, device=local, row0=r0, nrows_local=r1 - r0)
     if args.complex_storage:
         dev.set_option("real_mode", 0)
+    for kv in args.option:
+        k, v = kv.split("=")
+        dev.set_option(k, int(v))
     dev.set_timing(True)
     dev.connect(comm, part)
     dev.set_halo(plan.ghost_cols)
     dev.set_csr(plan.indptr, plan.indices, plan.data)
     dev.set_columns(0, v0[r0:r1])
+    host_ms = []
 
     def grow(start):
         cols, n_iter, brk = dev.expand(start, MAX_DIM, TOL)
@@ -436,10 +646,10 @@ def run_b200_multi(args, rank, world, local):
 
     def cycle():
         m = MAX_DIM
-        T1, Q1 = schur(H[:m, :m], output="complex")
-        T2, Q2 = ordered_schur(T1, output="complex", sort_function=arg_largest_real)
-        Q = Q1 @ Q2
+        t0 = time.perf_counter()
+        T2, Q = rotate(H[:m, :m], arg_largest_real)
         spike = H[m, :m] @ Q[:, :P]
+        host_ms.append(1e3 * (time.perf_counter() - t0))
         dev.restart(Q, m, P)
         H[:P, :P] = T2[:P, :P]
         H[P, :P] = spike
@@ -451,6 +661,7 @@ def run_b200_multi(args, rank, world, local):
         cycle()
     dev.synchronize()
     dev.reset_stats()
+    host_ms.clear()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
@@ -469,21 +680,16 @@ def run_b200_multi(args, rank, world, local):
     matvecs = args.steps * (MAX_DIM - P)
     value = matvecs / (ms_max * 1e-3)
     peak, peak_src = measured_peak()
-    classes = {}
-    for key in ("spmv", "ortho_pass1", "ortho_fused", "ortho_pass2", "restart"):
-        if st[key + "_launches"]:
-            classes[key] = dict(ms=st[key + "_ms"], bytes=st[key + "_bytes"],
-                                launches=st[key + "_launches"],
-                                gbs=st[key + "_bytes"] / st[key + "_ms"] / 1e6)
-    top = max(classes, key=lambda k: classes[k]["ms"])
-    kernels = {k: {"launches": v["launches"], "avg_ms": v["ms"] / v["launches"],
-                   "achieved_gbs": v["gbs"], "frac_of_measured": v["gbs"] / peak,
-                   "share_of_step": v["ms"] / ms} for k, v in classes.items()}
+    classes, top, kernels = kernel_table(st, ms, peak)
     roofline = {"bound": "hbm", "kernel": top, "achieved": classes[top]["gbs"], "peak": peak,
                 "unit": "GB/s", "frac": classes[top]["gbs"] / peak, "peak_source": peak_src,
                 "traffic": None, "kernels": kernels, "note": "rank 0, per-GPU bytes / per-GPU time",
+                "kernel_sum_ms_per_step": sum(v["ms"] for v in classes.values()) / args.steps,
+                "host_rotate_ms_per_step": float(np.mean(host_ms)),
                 "halo_entries_rank0": int(len(plan.ghost_cols))}
     launches = int(st["kernel_launches"])
+    dev.disconnect()
+    comm.barrier()
     dev.close()
 
     e2e = None
@@ -512,18 +718,21 @@ def run_b200_multi(args, rank, world, local):
                "call": f"partial_schur(A_host, {NEV}, max_dim={MAX_DIM}, max_restarts={restarts}, "
                        f"comm=...) = {mv} matvecs per call, {float(np.mean(times)):.3f} s per call "
                        "(max over ranks) incl. row slicing + halo plan on the host, uploads, "
-                       "local Q download", "reps": len(times),
+                       "local Q download; bytes are per CALL, summed over ranks",
+               "reps": len(times),
                "host_phases_s_rank0": {k: round(v, 4) for k, v in phases.items()}}
+    del A
+    converged = None if args.no_converged else converged_leg(None, comm=comm, device=local)
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_max / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": storage_note(st), "data": "synthetic",
-            "config": dict(workload_config(), parallelism=f"block-row x{world}")
-            if grid == GRID_FULL else {"workload": f"lap2d({grid}) REDUCED (not config 2)"},
+            "config": dict(workload_config(grid), parallelism=f"block-row x{world}"),
             "wall_ms_per_step": 1e3 * wall_max / args.steps,
-            "roofline": roofline, "cpu_baseline": None, "e2e": e2e,
+            "roofline": roofline, "cpu_baseline": None, "e2e": e2e, "converged": converged,
+            "parity": parity,
             "gpu_launches": launches, "clocks": clk,
         }
         print(json.dumps(line))
@@ -538,13 +747,18 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--grid", type=int, default=GRID_FULL, help="lap2d grid side (4096 = config 2)")
-    ap.add_argument("--e2e-restarts", type=int, default=24)
+    ap.add_argument("--e2e-restarts", type=int, default=60)
     ap.add_argument("--e2e-reps", type=int, default=1)
-    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--ref-cycles", type=int, default=2,
+                    help="restart cycles the reference arm times (one costs ~25 s of CPU)")
     ap.add_argument("--complex-storage", action="store_true",
                     help="keep the basis as complex128 even while it is provably real")
+    ap.add_argument("--option", action="append", default=[], metavar="KEY=INT",
+                    help="ab200_set_option for the value leg (A/B runs)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-converged", action="store_true")
     args = ap.parse_args()
     # stdout carries exactly ONE line (the JSON record): anything libraries print while the
     # benchmark runs (e.g. NCCL's version banner) is diverted to stderr at the fd level

@@ -209,16 +209,24 @@ def test_bench_reference_arm_prints_one_json_line():
     import json
     import subprocess
     import sys
+    env = dict(os.environ, OMP_NUM_THREADS="1")      # what torchrun exports to its children
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference",
-                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True,
-                         timeout=600)
+                          "--steps", "20", "--warmup", "5", "--grid", "192", "--no-converged"],
+                         capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1
     rec = json.loads(lines[0])
     assert rec["impl"] == "reference" and rec["unit"] == "matvec/s" and rec["value"] > 0
     assert rec["higher_is_better"] is True and rec["vs_baseline"] is None
-    assert rec["cpu_baseline"]["kind"] == "port" and rec["cpu_baseline"]["cores"] >= 1
+    ref_installed = os.path.exists(os.path.join(ROOT, "baseline", "_ref", "arnoldi", "__init__.py"))
+    assert rec["cpu_baseline"]["kind"] == ("reference" if ref_installed else "port")
+    # the launcher's OMP_NUM_THREADS=1 must not shrink the baseline to one core
+    assert rec["cpu_baseline"]["cores"] == (os.cpu_count() or 1)
+    # what the driver checks: steps x ms_per_step is the region that was really timed
+    assert rec["steps"] == 20 and rec["warmup"] == 5
+    assert abs(rec["steps"] * rec["ms_per_step"] * 1e-3 - rec["timed_region_s"]) < 1e-9
+    assert rec["timed_cycles"] == 2 and rec["timed_matvecs"] == 50
     assert rec["e2e"]["h2d_bytes_per_step"] == 0 and rec["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in rec["config"]
 
