@@ -72,6 +72,10 @@ struct SpmvArgs {
   int stages;              // shared-memory ring depth
   int rp_cap;              // row pointers staged per tile (multiple of 4)
   int bps;                 // resident blocks per SM to launch (0 = what fits)
+  // skewed rows with local columns (spmv_window_kernel): x entries of the tile's window that
+  // are staged in shared memory
+  int window;
+  int win_cap;
   // halo read straight from the owners' HBM (multi-GPU "pull"): ghost entry g of rank q lives at
   // peer_col[q][ghost_off[g]]; entries [seg_start[q], seg_start[q+1]) belong to rank q
   int direct_halo;
@@ -82,6 +86,12 @@ struct SpmvArgs {
 };
 
 cudaError_t launch_spmv(const SpmvArgs& a, int indptr_bits, int value_kind, cudaStream_t st);
+size_t spmv_window_smem(int win_cap, int rp_cap, int val_bytes, int idx_bytes, int x_bytes);
+// fraction (in 1/1024ths, over a sample of the rows) of the entries whose column lies within
+// `half` of their row: decides whether staging an x window in shared memory pays
+cudaError_t launch_spmv_locality(const void* indptr, int indptr_bits, const int32_t* indices, int64_t n,
+                                 int64_t n_local_cols, int64_t half, unsigned long long* out2,
+                                 cudaStream_t st);
 // builds rowblk[b] = first row whose indptr >= b * tile  (b = 0..nblocks), on device
 cudaError_t launch_spmv_maxrow(const void* indptr, int indptr_bits, int64_t n, int* out,
                                cudaStream_t st);

@@ -95,6 +95,8 @@ struct ab200_solver {
   int spmv_threads = 128;
   int spmv_algo = AB200_SPMV_AUTO;
   int spmv_stages = 3, spmv_rp_cap = 0;
+  int spmv_window = 0, spmv_win_cap = 0;   // skewed rows with local columns: x window in smem
+  int spmv_locality_pm = 0;                // per-mille of sampled entries within the window
   int max_row_len = 0;
   // user-supplied device operator (ab200_set_operator) instead of a CSR block
   ab200_apply_fn op_fn = nullptr;
@@ -130,7 +132,7 @@ struct ab200_solver {
   // options
   int opt_grid_mult = 0, opt_restart_variant = 0, opt_ortho_variant = 0, opt_spmv_tile = 0,
       opt_fused_ct = 0, opt_spmv_threads = 0, opt_fused_stages = 0, opt_fused_r = 0, opt_spmv_variant = 0,
-      opt_spmv_stages = 0, opt_spmv_bps = 0, opt_halo_fold = 1;
+      opt_spmv_stages = 0, opt_spmv_bps = 0, opt_halo_fold = 1, opt_spmv_window = 0;
   bool disconnected = false;
   // download path: two pinned bounce buffers + a copy stream (ab200_get_columns)
   void* bounce[2] = {nullptr, nullptr};
@@ -570,12 +572,34 @@ int ab200_set_csr(ab200_solver* s, const void* indptr, int indptr_bits, const in
     if (tile > 4096) tile = 4096;
     if (!short_rows && tile > 1280) tile = 1280;  // skewed rows: measured best on the power-law operator
   }
+  // Skewed rows: stage the x window of each tile in shared memory when most entries sit near
+  // the diagonal (sampled on the device); AB200_SPMV_MERGE asks for it regardless.
+  s->spmv_window = 0;
+  s->spmv_locality_pm = 0;
+  if (!short_rows && spmv_algo != AB200_SPMV_VECTOR && nnz > 0) {
+    const int want = s->opt_spmv_window > 0 ? s->opt_spmv_window : 8704;  // +-4096 and the tile's rows
+    unsigned long long* cnt = nullptr;
+    CU(cudaMalloc(&cnt, 2 * sizeof(unsigned long long)));
+    CU(cudaMemsetAsync(cnt, 0, 2 * sizeof(unsigned long long), s->stream));
+    CU(launch_spmv_locality(s->indptr, indptr_bits, s->indices, s->n, s->n_local_cols, (want - 512) / 2,
+                            cnt, s->stream));
+    unsigned long long h[2] = {0, 0};
+    CU(cudaMemcpyAsync(h, cnt, sizeof(h), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    cudaFree(cnt);
+    s->spmv_locality_pm = h[1] ? (int)(1000.0 * (double)h[0] / (double)h[1]) : 0;
+    if (spmv_algo == AB200_SPMV_MERGE || s->spmv_locality_pm >= 500) {
+      s->spmv_window = 1;
+      s->spmv_win_cap = (want + 15) / 16 * 16;
+      if (s->opt_spmv_tile <= 0) tile = 4096;
+    }
+  }
   tile = (tile + 7) / 8 * 8;
   s->spmv_threads = threads;
   // measured on lap2d(4096) / mark(4000): two stages of one-row-per-thread tiles are enough
   // (6.47 TB/s; 3 stages 6.30, 4 stages 5.83 -- deeper rings only take L1 away from the gathers)
   s->spmv_stages = s->opt_spmv_stages >= 2 && s->opt_spmv_stages <= 8 ? s->opt_spmv_stages : 2;
-  s->spmv_rp_cap = 2 * threads + 8;
+  s->spmv_rp_cap = s->spmv_window ? 1032 : 2 * threads + 8;
   int64_t nblk = (nnz + tile - 1) / tile;
   if (nblk < 1) nblk = 1;
   REQUIRE(nblk < (1ll << 30), "too many SpMV tiles");
@@ -784,6 +808,8 @@ static int enqueue_spmv(ab200_solver* s, const void* x, void* y, const double* x
   a.rp_cap = s->spmv_rp_cap;
   a.bps = s->opt_spmv_bps;
   a.nranks = s->nranks;
+  a.window = s->spmv_window && s->opt_spmv_variant == 0;
+  a.win_cap = s->spmv_win_cap;
   const double sv = s->value_kind == AB200_F64 ? 8.0 : 16.0;
   const double eb = a.real ? 8.0 : 16.0;
   const double bytes = (double)s->nnz * (sv + 4.0) + (double)s->n * (s->indptr_bits / 8 + 2.0 * eb) +
@@ -1418,6 +1444,8 @@ int ab200_set_option(ab200_solver* s, const char* key, int64_t value) {
     s->opt_spmv_bps = (int)value;
   else if (!strcmp(key, "halo_fold"))
     s->opt_halo_fold = (int)value;
+  else if (!strcmp(key, "spmv_window"))
+    s->opt_spmv_window = (int)value;
   else if (!strcmp(key, "fused_r"))
     s->opt_fused_r = (int)value;
   else if (!strcmp(key, "fused_stages"))

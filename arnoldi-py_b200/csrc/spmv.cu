@@ -526,6 +526,240 @@ __global__ void __launch_bounds__(288) spmv_bulk_kernel(SpmvArgs a) {
   }
 }
 
+// ------------------------------------------------------------------ skewed rows: x window in shared memory
+// For operators whose rows are long and uneven (BASELINE config 4: Pareto row lengths, columns in a
+// band around the diagonal plus a sparse far tail) the streaming roofline is not what limits the
+// tile kernel: ncu shows 10 sectors per gather request, L1 hit rate 7% -- every 8/16-byte x
+// entry costs a 32-byte sector through L2.  Here the block first pulls the WINDOW of x its tile
+// can touch around the diagonal into shared memory with one bulk copy (contiguous, so it runs at
+// copy speed and neighbouring tiles hit L2), then streams the tile's values / column ids through
+// a two-stage bulk-copy ring in sub-tiles; all threads first turn a sub-tile into products
+// (coalesced over the entries, x from the window, only out-of-window / ghost entries go to
+// global memory), then rows are summed from the products in stored order (one thread per row,
+// a warp for segments > 64 entries).  Work per block is balanced in non-zeros (the plan's tiles),
+// not in rows.  Rows of <= 16 entries are still summed in scipy's order (bit-identical).
+constexpr int kWinSub = 1024;      // entries per sub-tile
+constexpr int kWinLongSeg = 64;    // segments longer than this are summed by a warp
+
+struct WinHdr {
+  int64_t r0, r1;    // rows of the tile
+  int64_t k0, k1;    // its entries
+  int64_t wlo;       // first x entry held in the window
+  int wlen;          // entries held
+  int nrp;           // row pointers staged (from row r0a)
+  int rpoff;
+  int pad;
+};
+
+template <typename IdxT, typename ValT, typename XT>
+__global__ void __launch_bounds__(288) spmv_window_kernel(SpmvArgs a) {
+  if (a.ctl != nullptr && a.ctl->stop) return;
+  extern __shared__ __align__(128) unsigned char win_smem[];
+  const int nthr = blockDim.x - kWarp;
+  const int ncw = nthr >> 5;
+  const int wcap = a.win_cap;
+  const int rpc = a.rp_cap;
+  // layout: xwin | 2 x (vals | cols) | prod | rptr | long-row list | hdr | barriers
+  size_t off = 0;
+  XT* xwin = reinterpret_cast<XT*>(win_smem);
+  off += ((size_t)wcap * sizeof(XT) + 127) / 128 * 128;
+  unsigned char* ring = win_smem + off;
+  const size_t ring_stage = (size_t)kWinSub * (sizeof(ValT) + sizeof(int32_t));
+  off += 2 * ring_stage;
+  XT* prod = reinterpret_cast<XT*>(win_smem + off);
+  off += (size_t)kWinSub * sizeof(XT);
+  IdxT* srow = reinterpret_cast<IdxT*>(win_smem + off);
+  off += ((size_t)rpc * sizeof(IdxT) + 15) / 16 * 16;
+  int* s_long = reinterpret_cast<int*>(win_smem + off);   // [kWinSub / kWinLongSeg + 2] local row ids
+  off += sizeof(int) * (kWinSub / kWinLongSeg + 4);
+  off = (off + 15) / 16 * 16;
+  WinHdr* hdr = reinterpret_cast<WinHdr*>(win_smem + off);
+  off += sizeof(WinHdr);
+  off = (off + 7) / 8 * 8;
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(win_smem + off);
+  unsigned long long* win_full = bars;        // window + row pointers + header of a tile landed
+  unsigned long long* tile_done = bars + 1;   // every consumer warp is done with the tile
+  unsigned long long* ring_full = bars + 2;   // [2]
+  unsigned long long* ring_empty = bars + 4;  // [2]
+  __shared__ int s_nlong;
+
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    mbar_init(win_full, 1);
+    mbar_init(tile_done, ncw);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(ring_full + i, 1);
+      mbar_init(ring_empty + i, ncw);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  const IdxT* __restrict__ indptr = static_cast<const IdxT*>(a.indptr);
+  const ValT* __restrict__ values = static_cast<const ValT*>(a.values);
+  const int32_t* __restrict__ indices = a.indices;
+  const XT* __restrict__ x = static_cast<const XT*>(a.x);
+  const int64_t* __restrict__ rowblk = a.rowblk;
+  const int64_t* __restrict__ nnzblk = a.rowblk + a.nblocks + 1;
+  // contiguous share of the tiles for this block: neighbouring tiles share most of their window
+  const int per = (a.nblocks + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int b0 = (int)blockIdx.x * per;
+  const int b1 = b0 + per < a.nblocks ? b0 + per : a.nblocks;
+
+  if (tid >= nthr) {
+    // ---------------- producer warp (lane 0)
+    if (tid != nthr) return;
+    constexpr int RA = 16 / (int)sizeof(IdxT);
+    constexpr int XA = 16 / (int)sizeof(XT);  // x entries per 16 bytes
+    unsigned use0 = 0, use1 = 0;  // times each ring stage has been filled
+    for (int b = b0, t = 0; b < b1; ++b, ++t) {
+      if (t > 0) mbar_wait(tile_done, (unsigned)(t - 1) & 1u);
+      const int64_t r0 = rowblk[b], r1 = rowblk[b + 1];
+      const int64_t k0 = nnzblk[b], k1 = nnzblk[b + 1];
+      const int64_t nrows = r1 - r0;
+      int64_t half = ((int64_t)wcap - nrows) / 2;
+      if (half < 0) half = 0;
+      int64_t wlo = r0 - half;
+      if (wlo < 0) wlo = 0;
+      wlo &= ~(int64_t)(XA - 1);
+      int64_t whi = wlo + wcap;
+      if (whi > a.n_local_cols) whi = a.n_local_cols;
+      int64_t wlen = whi - wlo;
+      if (wlen < 0) wlen = 0;
+      const int64_t wcopy = (wlen + XA - 1) & ~(int64_t)(XA - 1);  // columns are padded to 16 elements
+      const int64_t r0a = r0 & ~(int64_t)(RA - 1);
+      int64_t nrp = nrows + 1 + (r0 - r0a);
+      if (nrp > rpc) nrp = rpc;
+      nrp = (nrp + RA - 1) & ~(int64_t)(RA - 1);
+      hdr->r0 = r0;
+      hdr->r1 = r1;
+      hdr->k0 = k0;
+      hdr->k1 = k1;
+      hdr->wlo = wlo;
+      hdr->wlen = (int)wlen;
+      hdr->nrp = (int)nrp;
+      hdr->rpoff = (int)(r0 - r0a);
+      const unsigned bw = (unsigned)(wcopy * sizeof(XT)), br = (unsigned)(nrp * sizeof(IdxT));
+      mbar_expect_tx(win_full, bw + br);
+      if (bw) bulk_g2s(xwin, x + wlo, bw, win_full);
+      bulk_g2s(srow, indptr + r0a, br, win_full);
+      // the tile's entries, sub-tile by sub-tile, from the 4-aligned address at or below k0
+      const int64_t ka = k0 & ~(int64_t)3;
+      for (int64_t cs = ka; cs < k1; cs += kWinSub) {
+        const int st = (int)(((cs - ka) / kWinSub) & 1);
+        const unsigned used = st ? use1 : use0;
+        if (used > 0) mbar_wait(ring_empty + st, (used - 1) & 1u);
+        int64_t cnt = k1 - cs;
+        if (cnt > kWinSub) cnt = kWinSub;
+        const unsigned nc = (unsigned)((cnt + 3) & ~(int64_t)3);
+        unsigned char* base = ring + (size_t)st * ring_stage;
+        mbar_expect_tx(ring_full + st, nc * (unsigned)(sizeof(ValT) + 4));
+        bulk_g2s(base, values + cs, nc * (unsigned)sizeof(ValT), ring_full + st);
+        bulk_g2s(base + (size_t)kWinSub * sizeof(ValT), indices + cs, nc * 4u, ring_full + st);
+        if (st) use1 += 1; else use0 += 1;
+      }
+    }
+    return;
+  }
+
+  // ---------------- consumers
+  const XT* __restrict__ ghost = static_cast<const XT*>(a.ghost);
+  XT* __restrict__ yout = static_cast<XT*>(a.y);
+  const int64_t nloc = a.n_local_cols;
+  const double xs = a.xscale ? *a.xscale : 1.0;
+  const int lane = tid & 31, warp = tid >> 5;
+  unsigned use0 = 0, use1 = 0;
+  for (int b = b0, t = 0; b < b1; ++b, ++t) {
+    mbar_wait(win_full, (unsigned)t & 1u);
+    const WinHdr h = *hdr;
+    const int64_t ka = h.k0 & ~(int64_t)3;
+    const int nrows = (int)(h.r1 - h.r0);
+    if (h.k1 == h.k0) {  // only empty rows
+      for (int rl = tid; rl < nrows; rl += nthr) yout[h.r0 + rl] = xzero<XT>();
+    }
+    for (int64_t cs = ka; cs < h.k1; cs += kWinSub) {
+      const int st = (int)(((cs - ka) / kWinSub) & 1);
+      mbar_wait(ring_full + st, (st ? use1 : use0) & 1u);
+      if (st) use1 += 1; else use0 += 1;
+      const ValT* sval = reinterpret_cast<const ValT*>(ring + (size_t)st * ring_stage);
+      const int32_t* scol =
+          reinterpret_cast<const int32_t*>(ring + (size_t)st * ring_stage + (size_t)kWinSub * sizeof(ValT));
+      int64_t ce = cs + kWinSub;
+      if (ce > h.k1) ce = h.k1;
+      const int cnt = (int)(ce - cs);
+      // ---- products, coalesced over the entries
+      for (int k = tid; k < cnt; k += nthr) {
+        const int64_t col = scol[k];
+        const int64_t wi = col - h.wlo;
+        XT xv;
+        if (wi >= 0 && wi < h.wlen)
+          xv = xwin[wi];
+        else
+          xv = (col < nloc) ? ld_ro(x + col) : ld_ro(ghost + (col - nloc));
+        prod[k] = vmul(sval[k], xv);
+      }
+      if (tid == 0) s_nlong = 0;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ring_empty + st);   // values / column ids of this stage are consumed
+      asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");   // products visible to all consumers
+      // ---- rows: one thread per row over the products, stored order
+      const int64_t lo_k = cs > h.k0 ? cs : h.k0;
+      for (int rl = tid; rl < nrows; rl += nthr) {
+        const int slot = h.rpoff + rl;
+        int64_t rs, re;
+        if (slot + 1 < h.nrp) {
+          rs = (int64_t)srow[slot];
+          re = (int64_t)srow[slot + 1];
+        } else {
+          rs = (int64_t)indptr[h.r0 + rl];
+          re = (int64_t)indptr[h.r0 + rl + 1];
+        }
+        if (re <= lo_k && !(rs == re && cs == ka)) continue;  // finished in an earlier sub-tile
+        if (rs >= ce && rs != re) continue;                    // starts in a later one
+        const int64_t lo = rs > lo_k ? rs : lo_k;
+        const int64_t hi = re < ce ? re : ce;
+        if (hi - lo > kWinLongSeg) {
+          const int q = atomicAdd(&s_nlong, 1);
+          s_long[q] = rl;
+          continue;
+        }
+        XT acc = (rs < lo_k) ? yout[h.r0 + rl] : xzero<XT>();
+        for (int k = (int)(lo - cs); k < (int)(hi - cs); ++k) acc = cadd_rn(acc, prod[k]);
+        if (re <= ce) acc = cscale(acc, xs);
+        yout[h.r0 + rl] = acc;
+      }
+      asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");   // the long-row list is complete
+      const int nlong = s_nlong;
+      for (int l = warp; l < nlong; l += ncw) {
+        const int rl = s_long[l];
+        const int slot = h.rpoff + rl;
+        int64_t rs, re;
+        if (slot + 1 < h.nrp) {
+          rs = (int64_t)srow[slot];
+          re = (int64_t)srow[slot + 1];
+        } else {
+          rs = (int64_t)indptr[h.r0 + rl];
+          re = (int64_t)indptr[h.r0 + rl + 1];
+        }
+        const int64_t lo = rs > lo_k ? rs : lo_k;
+        const int64_t hi = re < ce ? re : ce;
+        XT acc = xzero<XT>();
+        for (int k = (int)(lo - cs) + lane; k < (int)(hi - cs); k += kWarp) acc = cadd_rn(acc, prod[k]);
+        acc = warp_sum(acc);
+        if (lane == 0) {
+          XT tsum = (rs < lo_k) ? cadd_rn(yout[h.r0 + rl], acc) : acc;
+          if (re <= ce) tsum = cscale(tsum, xs);
+          yout[h.r0 + rl] = tsum;
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");   // products / list may be overwritten
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tile_done);
+  }
+}
+
 cudaError_t launch_spmv_maxrow(const void* indptr, int indptr_bits, int64_t n, int* out,
                                cudaStream_t st) {
   int64_t grid = (n + 255) / 256;
@@ -535,6 +769,45 @@ cudaError_t launch_spmv_maxrow(const void* indptr, int indptr_bits, int64_t n, i
     spmv_maxrow_kernel<int32_t><<<(int)grid, 256, 0, st>>>(static_cast<const int32_t*>(indptr), n, out);
   else
     spmv_maxrow_kernel<int64_t><<<(int)grid, 256, 0, st>>>(static_cast<const int64_t*>(indptr), n, out);
+  return cudaGetLastError();
+}
+
+template <typename IdxT>
+__global__ void spmv_locality_kernel(const IdxT* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                     int64_t n, int64_t nloc, int64_t half,
+                                     unsigned long long* __restrict__ out2) {
+  unsigned long long in = 0, tot = 0;
+  // every 16th row, a warp per sampled row
+  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = wid * 16; r < n; r += nw * 16) {
+    const int64_t rs = (int64_t)indptr[r], re = (int64_t)indptr[r + 1];
+    for (int64_t k = rs + lane; k < re; k += 32) {
+      const int64_t c = indices[k];
+      const int64_t d = c - r;
+      tot += 1;
+      if (c < nloc && d >= -half && d <= half) in += 1;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    in += __shfl_xor_sync(0xffffffffu, in, o);
+    tot += __shfl_xor_sync(0xffffffffu, tot, o);
+  }
+  if (lane == 0 && tot) {  // integer sums: order-independent
+    atomicAdd(out2, in);
+    atomicAdd(out2 + 1, tot);
+  }
+}
+cudaError_t launch_spmv_locality(const void* indptr, int indptr_bits, const int32_t* indices, int64_t n,
+                                 int64_t n_local_cols, int64_t half, unsigned long long* out2,
+                                 cudaStream_t st) {
+  if (indptr_bits == 32)
+    spmv_locality_kernel<int32_t><<<148 * 4, 256, 0, st>>>(static_cast<const int32_t*>(indptr), indices, n,
+                                                           n_local_cols, half, out2);
+  else
+    spmv_locality_kernel<int64_t><<<148 * 4, 256, 0, st>>>(static_cast<const int64_t*>(indptr), indices, n,
+                                                           n_local_cols, half, out2);
   return cudaGetLastError();
 }
 
@@ -624,8 +897,42 @@ static cudaError_t launch_spmv_bulk(const SpmvArgs& a, cudaStream_t st) {
               : launch_spmv_bulk_h<IdxT, ValT, XT, false>(a, st);
 }
 
+size_t spmv_window_smem(int win_cap, int rp_cap, int val_bytes, int idx_bytes, int x_bytes) {
+  size_t off = ((size_t)win_cap * x_bytes + 127) / 128 * 128;
+  off += 2 * (size_t)kWinSub * (val_bytes + 4);
+  off += (size_t)kWinSub * x_bytes;
+  off += ((size_t)rp_cap * idx_bytes + 15) / 16 * 16;
+  off += sizeof(int) * (kWinSub / kWinLongSeg + 4);
+  off = (off + 15) / 16 * 16;
+  off += sizeof(WinHdr);
+  off = (off + 7) / 8 * 8;
+  return off + 6 * sizeof(unsigned long long);
+}
+
+template <typename IdxT, typename ValT, typename XT>
+static cudaError_t launch_spmv_window(const SpmvArgs& a, cudaStream_t st) {
+  const size_t smem = spmv_window_smem(a.win_cap, a.rp_cap, sizeof(ValT), sizeof(IdxT), sizeof(XT));
+  const int threads = 256 + kWarp;
+  static PerDeviceOnce once;
+  if (once.first_use()) {
+    cudaFuncSetAttribute(spmv_window_kernel<IdxT, ValT, XT>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  }
+  int occ = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmv_window_kernel<IdxT, ValT, XT>, threads,
+                                                    smem) != cudaSuccess || occ < 1)
+    occ = 1;
+  if (a.bps > 0 && a.bps < occ) occ = a.bps;
+  int64_t grid = (int64_t)a.num_sms * occ;
+  if (grid > a.nblocks) grid = a.nblocks;
+  if (grid < 1) grid = 1;
+  spmv_window_kernel<IdxT, ValT, XT><<<(int)grid, threads, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
 template <typename IdxT, typename ValT, typename XT, int THREADS>
 static cudaError_t launch_spmv_tt(const SpmvArgs& a, cudaStream_t st) {
+  if (a.window) return launch_spmv_window<IdxT, ValT, XT>(a, st);
   if (!a.long_rows && a.variant == 0) return launch_spmv_bulk<IdxT, ValT, XT>(a, st);
   if (!a.long_rows && a.variant == 2) return launch_spmv_stream<IdxT, ValT, XT, THREADS>(a, st);
   return a.long_rows ? launch_spmv_ttl<IdxT, ValT, XT, THREADS, true>(a, st)

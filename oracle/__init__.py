@@ -18,6 +18,7 @@ from .krylov import (  # noqa: F401
     arg_largest_real,
     arnoldi_expand,
     cgs_dgks,
+    explicit_restarts_with_deflation,
     mgs_dgks,
     partial_schur,
     rand_unit_vector,

@@ -20,6 +20,7 @@ Functions (n-length ops first, control logic after):
 * ``arnoldi_expand``  -- ``decomposition.py:13-68``
 * ``sorted_schur``    -- ``utils.py:32-67``
 * ``partial_schur``   -- ``krylov_schur.py:10-114``
+* ``explicit_restarts_with_deflation`` -- ``explicit_restarts.py:63-168``
 """
 
 from __future__ import annotations
@@ -291,3 +292,63 @@ def partial_schur(A, nev, *, max_dim=None, stopping_criterion=None,
     if not done:
         raise ValueError("Has not converged !")
     return V[:, :nev], H[:nev, :nev], history
+
+
+# --------------------------------------------------------------------------
+# Explicit restarts with deflation
+# --------------------------------------------------------------------------
+def _mgs_sweep(basis, w, tol):
+    """``explicit_restarts.py:63-77``: one modified Gram-Schmidt sweep, then normalise."""
+    for j in range(basis.shape[1]):
+        w -= np.vdot(basis[:, j], w) * basis[:, j]
+    beta = np.linalg.norm(w)
+    assert beta > tol, "MGS: Too small norm when orthornormalizing"
+    w /= beta
+    return w
+
+
+def explicit_restarts_with_deflation(A, nev, *, max_dim=None, stopping_criterion=None,
+                                     max_restarts=100, sort_function=None):
+    """``explicit_restarts.py:80-168``: one eigenpair after the other; Arnoldi from column k,
+    leading Ritz vector of the active block back into column k, MGS against the locked
+    columns, until its residual estimate passes; H column of the locked vector by explicit
+    projection; eigenpairs of the final nev x nev block."""
+    tol = np.sqrt(np.finfo(A.dtype).eps) if stopping_criterion is None else stopping_criterion
+    if sort_function is None:
+        sort_function = arg_largest_magnitude
+    assert max_restarts > 0
+    n = A.shape[0]
+    assert A.shape[1] == n
+    if max_dim is None:
+        max_dim = min(max(2 * nev + 1, 20), n)
+    V = np.zeros((n, max_dim + 1), dtype=np.complex128)
+    H = np.zeros((max_dim + 1, max_dim), dtype=np.complex128)
+    history = History.from_k(nev)
+    for k in range(nev):
+        v0 = rand_unit_vector(n, np.complex128)
+        _mgs_sweep(V[:, :k], v0, tol)
+        V[:, k] = v0
+        for restart in range(max_restarts):
+            _, _, m = arnoldi_expand(A, V, H, tol, start_dim=k)
+            assert m > k
+            lucky = m != max_dim
+            matvecs = restart * (max_dim - k) + (m - k)
+            Hk = H[k:, k:]
+            w, S = np.linalg.eig(Hk[: m - k, : m - k])         # decomposition.py:123-126
+            ind = sort_function(w)[: m - k]
+            S = S[:, ind]
+            values = w[ind]
+            resid = np.abs(Hk[m - k, m - k - 1] * S[-1])       # decomposition.py:129
+            V[:, k] = V[:, k:m] @ S[:, 0]
+            _mgs_sweep(V[:, :k], V[:, k], tol)
+            if lucky or (resid / np.abs(values))[0] < tol:
+                for i in range(k + 1):
+                    H[i, k] = np.vdot(V[:, i], A @ V[:, k])
+                H[k + 1:-1, k] = 0
+                history.matvecs[k] = matvecs
+                history.restarts[k] = restart + 1
+                break
+        else:
+            raise ValueError(f"Could not converge for value {k}")
+    vals, Y = np.linalg.eig(H[:nev, :nev])
+    return vals, V[:, :nev] @ Y, history

@@ -49,6 +49,27 @@ def main():
                                                  stopping_criterion=1e-8, max_restarts=2000))
     put("mark200_s0", solve_record(ks, utils, mats.mark(200), 0, nev=20, max_dim=60,
                                    stopping_criterion=1e-8, max_restarts=2000))
+    # ---- explicit restarts with deflation (explicit_restarts.py:80-168) -------------
+    import arnoldi.explicit_restarts as er
+    ex = {}
+    for tag, A, kw in (("mark10", mats.mark(10), dict(nev=3, max_dim=10, stopping_criterion=1e-8)),
+                       ("mark20", mats.mark(20), dict(nev=4, max_dim=20, stopping_criterion=1e-8,
+                                                      max_restarts=400)),
+                       ("rect12", lap2d_rect(12, 13), dict(nev=4, max_dim=24, stopping_criterion=1e-9,
+                                                           max_restarts=400))):
+        np.random.seed(0)
+        nev = kw.pop("nev")
+        vals, vecs, hist = er.explicit_restarts_with_deflation(
+            A, nev, sort_function=utils.arg_largest_real, **kw)
+        for k, v in csr_parts(A).items():
+            ex[f"{tag}_{k}"] = v
+        ex[f"{tag}_vals"] = vals
+        ex[f"{tag}_vecs"] = vecs
+        ex[f"{tag}_hist_matvecs"] = hist.matvecs
+        ex[f"{tag}_hist_restarts"] = hist.restarts
+        ex[f"{tag}_res"] = np.linalg.norm(A @ vecs - vals * vecs, axis=0)
+        print("explicit", tag, "vals", vals, "restarts", hist.restarts, "res %.2e" % ex[f"{tag}_res"].max())
+    np.savez_compressed(os.path.join(OUT, "explicit.npz"), **ex)
     np.savez_compressed(os.path.join(OUT, "solves_r2.npz"), **sol)
     for tag in ("rect32_s0", "rect32_s1", "rect64_s0", "rect64_s1", "mark200_s0"):
         print(tag, "R=", sol[f"{tag}_hist_restarts"][:1], "true=", sol[f"{tag}_true_matvecs"],

@@ -64,7 +64,12 @@ class FakeDeviceSolver:
         fn = oracle.cgs_dgks if ortho == 0 else oracle.mgs_dgks
         w = self.V[:, col]
         h = np.zeros(max(ncols, 1), np.complex128)
-        if ncols:
+        if ncols and ortho == 1 and eta == 0.0:
+            # a single modified Gram-Schmidt sweep (explicit_restarts.py:63-77)
+            for j in range(ncols):
+                w -= np.vdot(self.V[:, j], w) * self.V[:, j]
+            beta = float(np.linalg.norm(w))
+        elif ncols:
             beta, _ = fn(w, self.V[:, :ncols], h, tol, eta)
         else:
             beta = float(np.linalg.norm(w))

@@ -395,3 +395,88 @@ def test_wide_basis_solve(gpu):
         assert np.abs(Q.conj().T @ Q - np.eye(70)).max() < 1e-11
     with pytest.raises(ValueError, match="limit of 256"):
         partial_schur(sp.eye_array(1000, format="csr"), 130)
+
+
+EXPLICIT = [("mark10", dict(nev=3, max_dim=10, stopping_criterion=1e-8)),
+            ("mark20", dict(nev=4, max_dim=20, stopping_criterion=1e-8, max_restarts=400)),
+            ("rect12", dict(nev=4, max_dim=24, stopping_criterion=1e-9, max_restarts=400))]
+
+
+@pytest.mark.parametrize("tag,kw", EXPLICIT, ids=[c[0] for c in EXPLICIT])
+def test_explicit_restarts_with_deflation(gpu, golden, tag, kw):
+    """explicit_restarts.py:80-168 on the device kernels against the reference's record: same
+    eigenvalues, residuals below the reference's test threshold, per-pair restart counts equal
+    or within one (the estimate that stops a pair sits at tol; summation order differs)."""
+    from arnoldi.explicit_restarts import explicit_restarts_with_deflation   # alias package
+    from arnoldi_b200.utils import arg_largest_real
+    g = golden("explicit")
+    A = csr_from_golden(g, tag)
+    kw = dict(kw)
+    nev = kw.pop("nev")
+    np.random.seed(0)
+    stats = {}
+    vals, vecs, hist = explicit_restarts_with_deflation(A, nev, sort_function=arg_largest_real,
+                                                        stats=stats, **kw)
+    ref = g[f"{tag}_vals"]
+    a, b = vals[np.argsort(-vals.real)], ref[np.argsort(-ref.real)]
+    assert (np.abs(a - b) / np.abs(b)).max() < 1e-7
+    res = np.linalg.norm(A @ vecs - vals * vecs, axis=0)
+    np.testing.assert_allclose(res, 0, rtol=1e-4, atol=1e-8)       # the reference's own criterion
+    print(tag, "restarts", hist.restarts, "reference", g[f"{tag}_hist_restarts"])
+    assert np.abs(hist.restarts.astype(int) - g[f"{tag}_hist_restarts"].astype(int)).max() <= 1
+    assert stats["mgs_launches"] > 0 and stats["restart_launches"] > 0
+    from arnoldi_b200.matrices import mark
+    with pytest.raises(ValueError, match="Could not converge for value 0"):
+        explicit_restarts_with_deflation(mark(10), 3, max_dim=5, stopping_criterion=1e-16,
+                                         max_restarts=10)
+
+
+def _local_skewed(n, rng, long_rows=()):
+    """Power-law row lengths with columns in a band around the diagonal plus a few far ones,
+    unsorted, with duplicates; optional very long rows and runs of empty rows."""
+    lens = np.minimum((rng.pareto(1.3, n) * 4).astype(np.int64) + 1, 700)
+    lens[100:400] = 0
+    for r, l in long_rows:
+        lens[r] = l
+    indptr = np.concatenate(([0], np.cumsum(lens)))
+    nnz = int(indptr[-1])
+    rows = np.repeat(np.arange(n), lens)
+    off = rng.integers(-3000, 3001, nnz)
+    far = rng.random(nnz) < 0.04
+    cols = np.where(far, rng.integers(0, n, nnz), (rows + off) % n)
+    return sp.csr_matrix((rng.uniform(-1, 1, nnz), cols.astype(np.int32), indptr.astype(np.int32)),
+                         shape=(n, n))
+
+
+@pytest.mark.parametrize("opts", [dict(), dict(spmv_tile=1024), dict(spmv_window=2048),
+                                  dict(spmv_tile=8192, spmv_bps=1)])
+def test_spmv_window_kernel(gpu, opts):
+    """Skewed rows with local columns (AB200_SPMV_MERGE / AUTO): x window in shared memory.
+    Rows of <= 16 entries stay bit-identical to scipy; longer ones within 1e-13 of the row's
+    absolute sum.  Real and complex vectors, complex values, rows longer than several tiles,
+    runs of empty rows."""
+    from arnoldi_b200.matrices import powerlaw
+    from arnoldi_b200.solver import DeviceSolver
+    rng = np.random.default_rng(12)
+    mats = {"powerlaw": powerlaw(120000), "local": _local_skewed(60000, rng, [(17, 30000), (50000, 9000)])}
+    Ac = _local_skewed(20000, rng)
+    Ac = Ac.astype(np.complex128)
+    Ac.data = Ac.data + 1j * rng.standard_normal(Ac.nnz)
+    mats["complex"] = Ac
+    for name, A in mats.items():
+        n = A.shape[0]
+        lens = np.diff(A.indptr)
+        short = lens <= 16
+        Aabs = abs(A.copy())
+        for algo in ("merge", "auto"):
+            with DeviceSolver(n, 2) as dev:
+                for k, v in opts.items():
+                    dev.set_option(k, v)
+                dev.set_csr(A.indptr, A.indices, A.data, algo=algo)
+                for x in (rng.standard_normal(n) + 1j * rng.standard_normal(n),
+                          rng.standard_normal(n).astype(np.complex128)):
+                    y = dev.spmv(x)
+                    ref = A @ x
+                    scale = Aabs @ np.abs(x)
+                    assert np.all(np.abs(y - ref) <= 1e-13 * scale + 1e-300), (name, algo, opts)
+                    np.testing.assert_array_equal(y[short], ref[short], err_msg=f"{name} {algo} {opts}")
