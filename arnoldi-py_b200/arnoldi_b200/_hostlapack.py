@@ -36,15 +36,22 @@ class NativeRotate:
         self.lib = _lib.load()
         self.zgees = _capsule_pointer("zgees")
         self.ztrexc = _capsule_pointer("ztrexc")
+        self.dgees = _capsule_pointer("dgees")
 
-    def __call__(self, Hm, sort_function):
+    def __call__(self, Hm, sort_function, real_ok=False):
         m = Hm.shape[0]
         T = np.array(Hm, dtype=np.complex128, order="F", copy=True)
         Q = np.empty((m, m), np.complex128, order="F")
-        info = self.lib.ab200_host_schur(self.zgees, m, T.ctypes.data_as(C.c_void_p),
-                                         Q.ctypes.data_as(C.c_void_p), None)
-        if info != 0:
-            raise np.linalg.LinAlgError(f"zgees failed with info = {info}")
+        if real_ok and not np.any(T.imag):
+            info = self.lib.ab200_host_schur_real(self.dgees, m, T.ctypes.data_as(C.c_void_p),
+                                                  Q.ctypes.data_as(C.c_void_p))
+            if info != 0:
+                raise np.linalg.LinAlgError(f"dgees failed with info = {info}")
+        else:
+            info = self.lib.ab200_host_schur(self.zgees, m, T.ctypes.data_as(C.c_void_p),
+                                             Q.ctypes.data_as(C.c_void_p), None)
+            if info != 0:
+                raise np.linalg.LinAlgError(f"zgees failed with info = {info}")
         perm = np.ascontiguousarray(sort_function(np.diag(T)), dtype=np.int64)
         assert perm.shape == (m,), "sort_function must return a permutation of all m indices"
         Q2 = np.empty((m, m), np.complex128, order="F")

@@ -74,7 +74,7 @@ def partial_schur(
     sort_function=None, p=None,
     ortho="cgs2", v0=None, device=0, stats=None, raise_on_no_convergence=True, comm=None,
     halo="auto", real_storage=True, real_arith="lossless", on_breakdown="raise", lock=False,
-    dynamic_p=False, spmv_algo="auto",
+    dynamic_p=False, spmv_algo="auto", fast_real_schur=False,
 ):
     """Partial Schur decomposition ``A Q = Q T`` of the ``nev`` wanted eigenvalues.
 
@@ -123,6 +123,11 @@ def partial_schur(
         are still orthogonalised against it).  The reference never locks.
     dynamic_p : True keeps ``p + min(#converged, (max_dim - p) // 2)`` vectors at a restart
         (ARPACK's adjustment); the reference keeps ``p`` (README.md:117 lists this as TODO).
+    fast_real_schur : True factors H_m with dgees + 2 x 2 block rotations instead of zgees while
+        H_m is real (real basis): a third of the host arithmetic of a restart, which is what the
+        GPUs wait for.  A valid ordered Schur form, but not the reference's bit for bit (signs /
+        phases of the Schur vectors, rounding): converged values agree, restart counts may move
+        by rounding noise exactly as they do between OpenBLAS builds.
     halo  : "pull" (each rank reads the remote entries of v it needs straight from peer HBM),
         "push" (the owner gathers locally and streams them into the peer's buffer) or "auto"
         (push when some rank's halo has more than 65 536 scattered entries)
@@ -298,7 +303,7 @@ def partial_schur(
             # rotate: zgees on H_m, then the reference's ordered_schur on the triangular result
             # (its second zgees is an exact no-op on triangular input and is skipped, its
             # ztrexc sequence is kept call for call so Q matches to rounding)
-            T2, Q = rotate(H[:m, :m], sort_function)
+            T2, Q = rotate(H[:m, :m], sort_function, fast_real=fast_real_schur and basis_real)
             last_beta = 0.0 if exhausted else H[m, m - 1]
 
             # convergence estimates |beta q_{m-1,k}| / |t_kk|     (krylov_schur.py:91-92)

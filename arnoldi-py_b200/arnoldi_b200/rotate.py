@@ -41,10 +41,15 @@ def _load_native():
     return _native
 
 
-def rotate(Hm, sort_function):
+def rotate(Hm, sort_function, fast_real=False):
     """Ordered complex Schur form of ``Hm``: returns ``(T2, Q)`` with ``Hm = Q T2 Q^H`` and
-    ``diag(T2)`` in the order ``sort_function`` asks for."""
+    ``diag(T2)`` in the order ``sort_function`` asks for.
+
+    ``fast_real``: when ``Hm`` has no imaginary part, factor it with dgees (a third of zgees's
+    arithmetic) and rotate the 2 x 2 blocks to triangular form.  The result is a valid ordered
+    Schur form but not bit-for-bit the reference's (signs / phases of the vectors, rounding),
+    so the driver only asks for it where it has left the reference's arithmetic anyway."""
     nat = _load_native()
     if nat:
-        return nat(Hm, sort_function)
+        return nat(Hm, sort_function, real_ok=fast_real)
     return rotate_scipy(Hm, sort_function)

@@ -151,6 +151,77 @@ __device__ __forceinline__ bool last_block_ticket(unsigned* ticket, unsigned nbl
   return *smem_flag != 0;
 }
 
+// ---------------------------------------------------------------- mbarrier / bulk copy (sm_90+)
+// SASS: SYNCS.* for the mbarrier operations, UBLKCP for cp.async.bulk.
+__device__ __forceinline__ unsigned smem_addr(const void* p) {
+  return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_addr(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// global -> shared bulk copy; dst, src and bytes are multiples of 16
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes,
+                                         unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_addr(dst)),
+      "l"(src), "r"(bytes), "r"(smem_addr(bar))
+      : "memory");
+}
+
+// ---------------------------------------------------------------- L2 eviction hints
+// Streams that are read exactly once (CSR values / column ids) are marked evict-first so they
+// do not push the gathered vector x -- which is re-read all the time -- out of L2.
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ cplx ld_stream_ef(const cplx* p, unsigned long long pol) {
+  cplx r;
+  asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;"
+      : "=d"(r.x), "=d"(r.y) : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ int4 ld_stream_ef(const int4* p, unsigned long long pol) {
+  int4 r;
+  asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0, %1, %2, %3}, [%4], %5;"
+      : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, unsigned bytes,
+                                              unsigned long long* bar, unsigned long long pol) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_addr(dst)),
+      "l"(src), "r"(bytes), "r"(smem_addr(bar)), "l"(pol)
+      : "memory");
+}
+
 // Function attributes (opt-in shared memory) are per device: remember per device ordinal
 // whether a launcher has configured its kernel yet.
 constexpr int kMaxDevices = 64;

@@ -10,6 +10,7 @@
 // routines, in the same order, through the addresses the caller hands in (the Python driver
 // takes them from scipy.linalg.cython_lapack -- the OpenBLAS the reference itself runs on).
 // The library itself links no LAPACK.
+#include <math.h>
 #include <stdint.h>
 #include <string.h>
 
@@ -26,6 +27,11 @@ typedef void (*zgees_t)(char* jobvs, char* sort, void* select, int* n, zc* a, in
 typedef void (*ztrexc_t)(char* compq, int* n, zc* t, int* ldt, zc* q, int* ldq, int* ifst,
                          int* ilst, int* info);
 
+typedef void (*dgees_t)(char* jobvs, char* sort, void* select, int* n, double* a, int* lda,
+                        int* sdim, double* wr, double* wi, double* vs, int* ldvs, double* work,
+                        int* lwork, int* bwork, int* info);
+
+thread_local std::vector<double> g_da, g_dvs, g_dwork, g_wr, g_wi;
 thread_local std::vector<zc> g_work;
 thread_local std::vector<double> g_rwork;
 thread_local std::vector<zc> g_w;
@@ -55,6 +61,90 @@ int ab200_host_schur(void* zgees_fn, int m, double* t, double* q, double* work) 
   zgees(&jobvs, &sort, nullptr, &n, reinterpret_cast<zc*>(t), &lda, &sdim, g_w.data(),
         reinterpret_cast<zc*>(q), &ldvs, g_work.data(), &lwork, g_rwork.data(), &bwork, &info);
   return info;
+}
+
+// Complex Schur form of a REAL matrix through the real routine: dgees (a third of zgees's
+// arithmetic), then every 2 x 2 block of the quasi-triangular factor -- a complex-conjugate
+// pair -- is triangularised by one complex Givens rotation (the construction of
+// scipy.linalg.rsf2csf).  With only real eigenvalues the result is real.  h: column-major
+// complex m x m whose imaginary parts are all zero (checked; AB200_EINVAL otherwise).
+// A valid Schur form of the same matrix as ab200_host_schur's, not the same one: diagonal
+// order before sorting, signs and phases of the vectors and the rounding differ.
+int ab200_host_schur_real(void* dgees_fn, int m, double* t, double* q) {
+  if (dgees_fn == nullptr || t == nullptr || q == nullptr || m < 1) return AB200_EINVAL;
+  dgees_t dgees = reinterpret_cast<dgees_t>(dgees_fn);
+  const size_t mm = (size_t)m * m;
+  g_da.resize(mm);
+  g_dvs.resize(mm);
+  g_wr.resize(m);
+  g_wi.resize(m);
+  for (size_t i = 0; i < mm; ++i) {
+    if (t[2 * i + 1] != 0.0) return AB200_EINVAL;
+    g_da[i] = t[2 * i];
+  }
+  char jobvs = 'V', sort = 'N';
+  int n = m, lda = m, ldvs = m, sdim = 0, info = 0, lwork = -1, bwork = 0;
+  double query = 0.0;
+  dgees(&jobvs, &sort, nullptr, &n, g_da.data(), &lda, &sdim, g_wr.data(), g_wi.data(),
+        g_dvs.data(), &ldvs, &query, &lwork, &bwork, &info);
+  if (info != 0) return info;
+  lwork = (int)query;
+  if (lwork < 3 * m) lwork = 3 * m;
+  if ((int)g_dwork.size() < lwork) g_dwork.resize(lwork);
+  dgees(&jobvs, &sort, nullptr, &n, g_da.data(), &lda, &sdim, g_wr.data(), g_wi.data(),
+        g_dvs.data(), &ldvs, g_dwork.data(), &lwork, &bwork, &info);
+  if (info != 0) return info;
+  zc* T = reinterpret_cast<zc*>(t);
+  zc* Z = reinterpret_cast<zc*>(q);
+  for (size_t i = 0; i < mm; ++i) {
+    T[i].re = g_da[i], T[i].im = 0.0;
+    Z[i].re = g_dvs[i], Z[i].im = 0.0;
+  }
+  auto at = [m](zc* M, int r, int c) -> zc& { return M[(size_t)c * m + r]; };
+  auto mul = [](zc a, zc b) { zc r = {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; return r; };
+  auto add = [](zc a, zc b) { zc r = {a.re + b.re, a.im + b.im}; return r; };
+  const double eps = 2.220446049250313e-16;
+  for (int k = m - 1; k >= 1; --k) {
+    const double sub = at(T, k, k - 1).re;
+    if (fabs(sub) <= eps * (fabs(at(T, k - 1, k - 1).re) + fabs(at(T, k, k).re))) {
+      at(T, k, k - 1).re = 0.0;
+      continue;
+    }
+    // eigenvalue (positive imaginary part) of the block minus its (k, k) entry
+    const double a = at(T, k - 1, k - 1).re, b = at(T, k - 1, k).re, d = at(T, k, k).re;
+    const double half = 0.5 * (a - d), disc = half * half + b * sub;
+    zc mu;
+    if (disc < 0.0) {
+      mu.re = half, mu.im = sqrt(-disc);
+    } else {  // a real pair left as a block: rotate to its larger root
+      mu.re = half + (half >= 0 ? sqrt(disc) : -sqrt(disc)), mu.im = 0.0;
+    }
+    const double r = sqrt(mu.re * mu.re + mu.im * mu.im + sub * sub);
+    const zc c = {mu.re / r, mu.im / r};
+    const zc cc = {c.re, -c.im};
+    const double sn = sub / r;
+    const zc s_p = {sn, 0.0}, s_m = {-sn, 0.0};
+    // T[k-1:k+1, k-1:] = G T[k-1:k+1, k-1:]   with G = [[conj(c), s], [-s, c]]
+    for (int j = k - 1; j < m; ++j) {
+      const zc x = at(T, k - 1, j), y = at(T, k, j);
+      at(T, k - 1, j) = add(mul(cc, x), mul(s_p, y));
+      at(T, k, j) = add(mul(s_m, x), mul(c, y));
+    }
+    // T[:k+1, k-1:k+1] = T[:k+1, k-1:k+1] G^H ;  Z[:, k-1:k+1] = Z[:, k-1:k+1] G^H
+    // G^H = [[c, -s], [s, conj(c)]]
+    for (int i = 0; i <= k; ++i) {
+      const zc x = at(T, i, k - 1), y = at(T, i, k);
+      at(T, i, k - 1) = add(mul(x, c), mul(y, s_p));
+      at(T, i, k) = add(mul(x, s_m), mul(y, cc));
+    }
+    for (int i = 0; i < m; ++i) {
+      const zc x = at(Z, i, k - 1), y = at(Z, i, k);
+      at(Z, i, k - 1) = add(mul(x, c), mul(y, s_p));
+      at(Z, i, k) = add(mul(x, s_m), mul(y, cc));
+    }
+    at(T, k, k - 1).re = 0.0, at(T, k, k - 1).im = 0.0;
+  }
+  return 0;
 }
 
 // perm[dest] = index (into the UNSORTED diagonal of T1) of the eigenvalue wanted at slot dest.

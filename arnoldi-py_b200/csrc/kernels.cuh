@@ -76,6 +76,7 @@ struct SpmvArgs {
   // are staged in shared memory
   int window;
   int win_cap;
+  int contig;              // tile kernel: persistent blocks over contiguous tile ranges (L1 reuse of x)
   // halo read straight from the owners' HBM (multi-GPU "pull"): ghost entry g of rank q lives at
   // peer_col[q][ghost_off[g]]; entries [seg_start[q], seg_start[q+1]) belong to rank q
   int direct_halo;

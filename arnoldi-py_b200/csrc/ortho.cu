@@ -588,6 +588,228 @@ __global__ void __launch_bounds__(CT < 5 ? 256 : 512) cgs_fused_kernel(OrthoArgs
   if (s_again) finish_dots(a, 0, c, red, false);
 }
 
+// ------------------------------------------------------------------ CGS fused pass, pipelined
+// Same sweep as cgs_fused_kernel (w' = w - U coef ; g' = U^H w' ; ||w'||^2) with the two block
+// barriers per chunk taken out.  ncu on cgs_fused_kernel: top stall = the __syncthreads around
+// the serial rebuild of w' (one warp works, the others wait, twice per chunk).  Here the
+// chunks are software-pipelined and the hand-offs are mbarriers that only the warp that needs
+// the data waits on:
+//
+//   every warp, iteration i :  partial sums of U coef for chunk i -> spart[i & 1]; arrive full[i & 1]
+//   rebuilder(i) = warp i % W:  wait full[i & 1]; w'(i) = w(i) - sum of partials -> swp[i & 1],
+//                               global store, norm; arrive ready[i & 1]
+//   every warp, iteration i :  wait ready[(i-1) & 1]; dots of chunk i-1 against w'(i-1)
+//
+// so while one warp rebuilds w'(i) the others already run the dots of chunk i-1 and the partial
+// sums of chunk i+1: nobody idles at a block-wide rendezvous.  U is staged by cp.async into a
+// 3-slot ring (each warp refills only its own columns' slice, so the ring needs no barrier);
+// the dots re-read their chunk from the ring instead of holding it in registers.
+template <int CT, int R, bool REAL, int MAXT>
+__global__ void __launch_bounds__(MAXT) cgs_fused_pipe_kernel(OrthoArgs a) {
+  StepCtl* ctl = a.ctl;
+  if (ctl->stop) return;
+
+  constexpr int ROWS = kWarp * R;
+  constexpr int S = 2;
+  extern __shared__ __align__(16) unsigned char fused_smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nwarps = blockDim.x >> 5;
+  const int c = a.ncols;
+  cplx* spart = reinterpret_cast<cplx*>(fused_smem);  // [2][nwarps][ROWS]
+  cplx* scoef = spart + 2 * nwarps * ROWS;            // [nwarps * CT]
+  cplx* swp = scoef + nwarps * CT;                    // [2][ROWS]            w' of a chunk
+  cplx* sw = swp + 2 * ROWS;                          // [4][ROWS]            chunk of w
+  cplx* sv = sw + 4 * ROWS;                           // [S][nwarps][CT][ROWS] chunk of U
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(sv + (size_t)S * nwarps * CT * ROWS);
+  unsigned long long* full = bars;       // [2] partial sums of a chunk are complete
+  unsigned long long* ready = bars + 2;  // [2] w' of a chunk is published
+  for (int i = threadIdx.x; i < nwarps * CT; i += blockDim.x)
+    scoef[i] = i < c ? a.coef[i] : make_double2(0.0, 0.0);
+  if (threadIdx.x == 0) {
+    // full: one arrival per warp (the rebuilder counts itself); ready: the rebuilder alone
+    mbar_init(full, nwarps), mbar_init(full + 1, nwarps);
+    mbar_init(ready, 1), mbar_init(ready + 1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int mycol0 = warp * CT;
+  int mycols = c - mycol0;
+  mycols = mycols < 0 ? 0 : (mycols > CT ? CT : mycols);
+  const int64_t ld = a.ld;
+  cplx* w = a.w;
+  const cplx* __restrict__ U = a.U + (int64_t)mycol0 * ld;
+  cplx cf[CT];
+#pragma unroll
+  for (int k = 0; k < CT; ++k) cf[k] = scoef[mycol0 + k];
+  cplx acc[CT];
+#pragma unroll
+  for (int k = 0; k < CT; ++k) acc[k] = make_double2(0.0, 0.0);
+  double nacc = 0.0;
+
+  const int64_t nchunks = (a.n + ROWS - 1) / ROWS;
+  const int64_t nit = nchunks > blockIdx.x ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  auto chunk_of = [&](int64_t i) { return (int64_t)blockIdx.x + i * gridDim.x; };
+  // chunk i: my columns -> sv[i % 2][warp] (a slice only its own warp touches); warp 0 also
+  // stages w, in a 4-slot ring: chunk i + 4 is staged in iteration i + 2, i.e. after warp 0 ran
+  // the dots of chunk i, which waited for the rebuilder of chunk i -- the reader of w(i)
+  auto stage = [&](int64_t i) {
+    if (i < nit) {
+      const int64_t base = chunk_of(i) * ROWS + lane;
+      cplx* dst = sv + ((size_t)(i % S) * nwarps + warp) * CT * ROWS;
+#pragma unroll
+      for (int k = 0; k < CT; ++k) {
+        if (k < mycols) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const int64_t row = base + r * kWarp;
+            const bool ok = row < a.n;
+            cp_async16(dst + k * ROWS + r * kWarp + lane, U + (int64_t)k * ld + (ok ? row : 0), ok);
+          }
+        }
+      }
+      if (warp == 0) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int64_t row = base + r * kWarp;
+          const bool ok = row < a.n;
+          cp_async16(sw + (size_t)(i % 4) * ROWS + r * kWarp + lane, w + (ok ? row : 0), ok);
+        }
+      }
+    }
+    cp_async_commit();
+  };
+
+  cplx vold[CT][R];  // chunk i - 1 of my columns, kept for its dots
+  stage(0);
+  stage(1);
+  for (int64_t i = 0; i <= nit; ++i) {
+    const int b = (int)(i & 1);
+    cplx v[CT][R];
+    if (i < nit) {
+      cp_async_wait<1>();  // chunk i has landed (chunk i + 1 may still be in flight)
+      __syncwarp();
+      const cplx* src = sv + ((size_t)(i % S) * nwarps + warp) * CT * ROWS;
+#pragma unroll
+      for (int k = 0; k < CT; ++k)
+        if (k < mycols) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) v[k][r] = src[k * ROWS + r * kWarp + lane];
+        }
+      __syncwarp();
+      stage(i + 2);  // the slice just read into registers is free: refill it
+      // ---- my columns' share of U coef for chunk i
+      cplx* mine = spart + ((size_t)b * nwarps + warp) * ROWS;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        cplx t = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int k = 0; k < CT; ++k)
+          if (k < mycols) addax<REAL>(t, v[k][r], cf[k]);
+        mine[r * kWarp + lane] = t;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full + b);  // release: my partial sums (and warp 0's chunk of w)
+      // ---- the rebuilder of chunk i
+      if (warp == (int)(i % nwarps)) {
+        mbar_wait(full + b, (unsigned)((i >> 1) & 1));
+        const int64_t base = chunk_of(i) * ROWS + lane;
+        const bool fullchunk = chunk_of(i) * ROWS + ROWS <= a.n;
+        const cplx* all = spart + (size_t)b * nwarps * ROWS;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          cplx wv = sw[(size_t)(i % 4) * ROWS + r * kWarp + lane];
+          cplx t = make_double2(0.0, 0.0);
+          for (int k2 = 0; k2 < nwarps; ++k2) t = cadd(t, all[k2 * ROWS + r * kWarp + lane]);
+          wv.x -= t.x;
+          wv.y -= t.y;
+          swp[b * ROWS + r * kWarp + lane] = wv;
+          const bool ok = fullchunk || base + r * kWarp < a.n;
+          if (ok) {
+            st_stream(w + base + r * kWarp, wv);
+            nacc = fma(wv.x, wv.x, nacc);
+            nacc = fma(wv.y, wv.y, nacc);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ready + b);  // release: w'(i) is in swp[b]
+      }
+    } else {
+      cp_async_commit();
+    }
+    // ---- dots of the previous chunk (its w' was rebuilt while this warp did the work above)
+    if (i > 0) {
+      const int64_t j = i - 1;
+      const int bj = (int)(j & 1);
+      if (warp != (int)(j % nwarps)) mbar_wait(ready + bj, (unsigned)((j >> 1) & 1));
+      cplx wv[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) wv[r] = swp[bj * ROWS + r * kWarp + lane];
+#pragma unroll
+      for (int k = 0; k < CT; ++k) {
+        if (k < mycols) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) dotacc<REAL>(acc[k], vold[k][r], wv[r]);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < CT; ++k)
+#pragma unroll
+      for (int r = 0; r < R; ++r) vold[k][r] = v[k][r];
+  }
+  cp_async_wait<0>();
+
+  const int gcap = a.grid_cap;
+#pragma unroll
+  for (int k = 0; k < CT; ++k) {
+    if (k < mycols) {
+      cplx s = warp_sum(acc[k]);
+      if (lane == 0) a.part[(size_t)(mycol0 + k) * gcap + blockIdx.x] = s;
+    }
+  }
+  __shared__ double s_nw[16];
+  {
+    double s = warp_sum(nacc);
+    if (lane == 0) s_nw[warp] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int k = 0; k < nwarps; ++k) t += s_nw[k];
+    a.npart[blockIdx.x] = t;
+  }
+
+  __shared__ int s_last;
+  __shared__ int s_again;
+  if (!last_block_ticket(a.ticket, gridDim.x, &s_last)) return;
+
+  double* red = reinterpret_cast<double*>(fused_smem);  // 2*c + 1 doubles (spart is free now)
+  for (int i = warp; i < c; i += nwarps) {
+    cplx g = sum_partials(a.part + (size_t)i * gcap, gridDim.x, lane);
+    if (lane == 0) {
+      red[2 * i] = g.x;
+      red[2 * i + 1] = g.y;
+    }
+  }
+  if (warp == 0) {
+    double s = sum_partials(a.npart, gridDim.x, lane);
+    if (lane == 0) red[2 * c] = s;
+  }
+  __syncthreads();
+  peer_allreduce(a.comm, red, 2 * c + 1, ctl);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double beta = sqrt(red[2 * c]);
+    const bool again = dgks_decide(a, beta);
+    if (!again) finalize_step(a, beta);
+    s_again = again ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_again) finish_dots(a, 0, c, red, false);
+}
+
 // ------------------------------------------------------------------ CGS fused pass, warp tiles
 // Same mathematics as cgs_fused_kernel (w' = w - U coef ; g' = U^H w' ; ||w'||^2 in one sweep),
 // different decomposition: every WARP owns a chunk of 32 elements x ALL c columns, staged into
@@ -1023,6 +1245,45 @@ static cudaError_t launch_fused_warp(const OrthoArgs& a, int num_sms, cudaStream
                 : launch_fused_warp_t<CMAX, false>(a, num_sms, st, gm);
 }
 
+template <int CT, int R, bool REAL, int MAXT>
+static cudaError_t launch_fused_pipe_trm(const OrthoArgs& a, int warps, int num_sms, cudaStream_t st,
+                                         int grid_mult) {
+  OrthoArgs args = a;
+  args.accumulate = 1;
+  const int threads = warps * kWarp;
+  constexpr int ROWS = kWarp * R;
+  const int64_t nchunks = (a.n + ROWS - 1) / ROWS;
+  size_t smem = sizeof(cplx) * ((size_t)2 * warps * ROWS + (size_t)warps * CT + 2 * ROWS + 4 * ROWS +
+                                (size_t)2 * warps * CT * ROWS) + 4 * sizeof(unsigned long long);
+  const size_t need = sizeof(double) * (2 * a.ncols + 2);
+  if (smem < need) smem = need;
+  static int occ[17] = {0};
+  static PerDeviceOnce once;
+  if (once.first_use()) {
+    cudaFuncSetAttribute(cgs_fused_pipe_kernel<CT, R, REAL, MAXT>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  }
+  const int bps = grid_mult > 0 ? grid_mult
+                                : resident_blocks(cgs_fused_pipe_kernel<CT, R, REAL, MAXT>, threads, smem,
+                                                  &occ[warps]);
+  const int grid = pick_grid(nchunks, bps, num_sms, a.grid_cap);
+  cgs_fused_pipe_kernel<CT, R, REAL, MAXT><<<grid, threads, smem, st>>>(args);
+  return cudaGetLastError();
+}
+template <int CT, int R, bool REAL>
+static cudaError_t launch_fused_pipe_tr(const OrthoArgs& a, int warps, int num_sms, cudaStream_t st,
+                                        int grid_mult) {
+  // up to 8 warps: a 256-thread bound leaves the registers for two chunks of U per lane
+  return warps <= 8 ? launch_fused_pipe_trm<CT, R, REAL, 256>(a, warps, num_sms, st, grid_mult)
+                    : launch_fused_pipe_trm<CT, R, REAL, 512>(a, warps, num_sms, st, grid_mult);
+}
+template <int CT, int R>
+static cudaError_t launch_fused_pipe_t(const OrthoArgs& a, int warps, int num_sms, cudaStream_t st,
+                                       int grid_mult) {
+  return a.real ? launch_fused_pipe_tr<CT, R, true>(a, warps, num_sms, st, grid_mult)
+                : launch_fused_pipe_tr<CT, R, false>(a, warps, num_sms, st, grid_mult);
+}
+
 // variant 0: cp.async-staged (prefetching) kernel; variant 2: register loads only.
 // fused_ct > 0 forces the column-tile width (when the block shape allows it).
 cudaError_t launch_cgs_fused(const OrthoArgs& a, int num_sms, cudaStream_t st, int grid_mult,
@@ -1053,6 +1314,25 @@ cudaError_t launch_cgs_fused(const OrthoArgs& a, int num_sms, cudaStream_t st, i
   // still leave two blocks per SM
   const int rr = ct <= 5 ? 2 : 1;
   const size_t stage_bytes = (size_t)2 * warps * ct * rr * kWarp * sizeof(cplx);
+  // variant 5: the mbarrier-pipelined sweep
+  if (variant == 5 && warps >= 3 && stage_bytes <= 96 * 1024) {
+    const int r1 = a.fused_r == 1 ? 1 : rr;
+    switch (ct) {
+      case 1: return r1 == 1 ? launch_fused_pipe_t<1, 1>(a, warps, num_sms, st, grid_mult)
+                             : launch_fused_pipe_t<1, 2>(a, warps, num_sms, st, grid_mult);
+      case 2: return r1 == 1 ? launch_fused_pipe_t<2, 1>(a, warps, num_sms, st, grid_mult)
+                             : launch_fused_pipe_t<2, 2>(a, warps, num_sms, st, grid_mult);
+      case 3: return r1 == 1 ? launch_fused_pipe_t<3, 1>(a, warps, num_sms, st, grid_mult)
+                             : launch_fused_pipe_t<3, 2>(a, warps, num_sms, st, grid_mult);
+      case 4: return r1 == 1 ? launch_fused_pipe_t<4, 1>(a, warps, num_sms, st, grid_mult)
+                             : launch_fused_pipe_t<4, 2>(a, warps, num_sms, st, grid_mult);
+      case 5: return r1 == 1 ? launch_fused_pipe_t<5, 1>(a, warps, num_sms, st, grid_mult)
+                             : launch_fused_pipe_t<5, 2>(a, warps, num_sms, st, grid_mult);
+      case 6: return launch_fused_pipe_t<6, 1>(a, warps, num_sms, st, grid_mult);
+      case 7: return launch_fused_pipe_t<7, 1>(a, warps, num_sms, st, grid_mult);
+      default: return launch_fused_pipe_t<8, 1>(a, warps, num_sms, st, grid_mult);
+    }
+  }
   if (variant != 2 && a.fused_r == 1) {  // A/B: one row pair per lane and chunk
     switch (ct) {
       case 3: return launch_fused_t<3, 1, true>(a, warps, num_sms, st, grid_mult);

@@ -588,7 +588,10 @@ int ab200_set_csr(ab200_solver* s, const void* indptr, int indptr_bits, const in
     CU(cudaStreamSynchronize(s->stream));
     cudaFree(cnt);
     s->spmv_locality_pm = h[1] ? (int)(1000.0 * (double)h[0] / (double)h[1]) : 0;
-    if (spmv_algo == AB200_SPMV_MERGE || s->spmv_locality_pm >= 500) {
+    // measured (powerlaw n = 1e7, real storage): the window kernel reaches 1.3-1.6 TB/s against
+    // 1.7 TB/s for the tile kernel (its tiles serialise on the window load and on the far
+    // gathers), so AUTO keeps the tile kernel; AB200_SPMV_MERGE selects the window kernel
+    if (spmv_algo == AB200_SPMV_MERGE) {
       s->spmv_window = 1;
       s->spmv_win_cap = (want + 15) / 16 * 16;
       if (s->opt_spmv_tile <= 0) tile = 4096;
@@ -809,6 +812,7 @@ static int enqueue_spmv(ab200_solver* s, const void* x, void* y, const double* x
   a.bps = s->opt_spmv_bps;
   a.nranks = s->nranks;
   a.window = s->spmv_window && s->opt_spmv_variant == 0;
+  a.contig = s->opt_spmv_variant == 3 ? 1 : 0;
   a.win_cap = s->spmv_win_cap;
   const double sv = s->value_kind == AB200_F64 ? 8.0 : 16.0;
   const double eb = a.real ? 8.0 : 16.0;

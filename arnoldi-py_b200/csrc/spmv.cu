@@ -122,8 +122,15 @@ __global__ void __launch_bounds__(kSpmvThreads) spmv_tile_kernel(SpmvArgs a) {
   const double xs = a.xscale ? *a.xscale : 1.0;
   const int tid = threadIdx.x;
   const int tile = a.tile;
+  const unsigned long long l2pol = l2_policy_evict_first();  // CSR streams must not evict x from L2
 
-  for (int b = blockIdx.x; b < a.nblocks; b += gridDim.x) {
+  // a.contig: each block walks a CONTIGUOUS range of tiles, so the x entries its SM gathers
+  // slide along the band of the operator and stay in L1 (otherwise: one tile per block)
+  const int per = a.contig ? (a.nblocks + (int)gridDim.x - 1) / (int)gridDim.x : 1;
+  const int bfirst = a.contig ? (int)blockIdx.x * per : (int)blockIdx.x;
+  const int bstep = a.contig ? 1 : (int)gridDim.x;
+  const int blast = a.contig ? (bfirst + per < a.nblocks ? bfirst + per : a.nblocks) : a.nblocks;
+  for (int b = bfirst; b < blast; b += bstep) {
     const int64_t r0 = a.rowblk[b], r1 = a.rowblk[b + 1];
     if (r0 >= r1) continue;
     const int64_t s = (int64_t)indptr[r0], e = (int64_t)indptr[r1];
@@ -141,16 +148,17 @@ __global__ void __launch_bounds__(kSpmvThreads) spmv_tile_kernel(SpmvArgs a) {
       {
         const int nvec = tot >> 2;
         const int4* c4 = reinterpret_cast<const int4*>(indices + ca);
-        for (int k = tid; k < nvec; k += kSpmvThreads) reinterpret_cast<int4*>(scol)[k] = __ldg(c4 + k);
+        for (int k = tid; k < nvec; k += kSpmvThreads)
+          reinterpret_cast<int4*>(scol)[k] = ld_stream_ef(c4 + k, l2pol);
         for (int k = (nvec << 2) + tid; k < tot; k += kSpmvThreads) scol[k] = indices[ca + k];
         const double2* v2 = reinterpret_cast<const double2*>(values + ca);
         if (sizeof(ValT) == 8) {
           for (int k = tid; k < (tot >> 1); k += kSpmvThreads)
-            reinterpret_cast<double2*>(sval)[k] = ld_stream(v2 + k);
+            reinterpret_cast<double2*>(sval)[k] = ld_stream_ef(v2 + k, l2pol);
           if ((tot & 1) && tid == 0) sval[tot - 1] = values[ca + tot - 1];
         } else {
           for (int k = tid; k < tot; k += kSpmvThreads)
-            reinterpret_cast<double2*>(sval)[k] = ld_stream(v2 + k);
+            reinterpret_cast<double2*>(sval)[k] = ld_stream_ef(v2 + k, l2pol);
         }
       }
       __syncthreads();
@@ -328,46 +336,6 @@ __global__ void __launch_bounds__(THREADS) spmv_stream_kernel(SpmvArgs a) {
 // (complete_tx); the consumer warps only wait, gather and accumulate, and hand the stage back
 // through a second mbarrier.  No block-wide barrier in the loop: warps drift apart by up to
 // `stages - 1` tiles.
-__device__ __forceinline__ unsigned smem_addr(const void* p) {
-  return (unsigned)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
-  unsigned ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(ok)
-      : "r"(smem_addr(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-  while (!mbar_try_wait(bar, parity)) {
-  }
-}
-// global -> shared bulk copy; dst, src and bytes are multiples of 16
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes,
-                                         unsigned long long* bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-          smem_addr(dst)),
-      "l"(src), "r"(bytes), "r"(smem_addr(bar))
-      : "memory");
-}
-
 struct TileHdr {   // written by the producer before it arms the stage's barrier
   int64_t ca;      // nnz index staged at slot 0 (4-entry aligned, <= first entry of the tile)
   int64_t r0;      // first row of the tile
@@ -613,6 +581,7 @@ __global__ void __launch_bounds__(288) spmv_window_kernel(SpmvArgs a) {
     constexpr int RA = 16 / (int)sizeof(IdxT);
     constexpr int XA = 16 / (int)sizeof(XT);  // x entries per 16 bytes
     unsigned use0 = 0, use1 = 0;  // times each ring stage has been filled
+    const unsigned long long l2pol = l2_policy_evict_first();
     for (int b = b0, t = 0; b < b1; ++b, ++t) {
       if (t > 0) mbar_wait(tile_done, (unsigned)(t - 1) & 1u);
       const int64_t r0 = rowblk[b], r1 = rowblk[b + 1];
@@ -655,8 +624,8 @@ __global__ void __launch_bounds__(288) spmv_window_kernel(SpmvArgs a) {
         const unsigned nc = (unsigned)((cnt + 3) & ~(int64_t)3);
         unsigned char* base = ring + (size_t)st * ring_stage;
         mbar_expect_tx(ring_full + st, nc * (unsigned)(sizeof(ValT) + 4));
-        bulk_g2s(base, values + cs, nc * (unsigned)sizeof(ValT), ring_full + st);
-        bulk_g2s(base + (size_t)kWinSub * sizeof(ValT), indices + cs, nc * 4u, ring_full + st);
+        bulk_g2s_hint(base, values + cs, nc * (unsigned)sizeof(ValT), ring_full + st, l2pol);
+        bulk_g2s_hint(base + (size_t)kWinSub * sizeof(ValT), indices + cs, nc * 4u, ring_full + st, l2pol);
         if (st) use1 += 1; else use0 += 1;
       }
     }
@@ -688,16 +657,31 @@ __global__ void __launch_bounds__(288) spmv_window_kernel(SpmvArgs a) {
       int64_t ce = cs + kWinSub;
       if (ce > h.k1) ce = h.k1;
       const int cnt = (int)(ce - cs);
-      // ---- products, coalesced over the entries
-      for (int k = tid; k < cnt; k += nthr) {
-        const int64_t col = scol[k];
-        const int64_t wi = col - h.wlo;
-        XT xv;
-        if (wi >= 0 && wi < h.wlen)
-          xv = xwin[wi];
-        else
-          xv = (col < nloc) ? ld_ro(x + col) : ld_ro(ghost + (col - nloc));
-        prod[k] = vmul(sval[k], xv);
+      // ---- products, coalesced over the entries; the (few) gathers that miss the window are
+      //      issued together so a thread waits for global memory once per sub-tile, not per entry
+      constexpr int PU = 4;
+      for (int k0 = tid; k0 < cnt; k0 += PU * nthr) {
+        XT xg[PU];
+        int64_t wi[PU];
+#pragma unroll
+        for (int u = 0; u < PU; ++u) {
+          const int k = k0 + u * nthr;
+          wi[u] = -1;
+          xg[u] = xzero<XT>();
+          if (k < cnt) {
+            const int64_t col = scol[k];
+            wi[u] = col - h.wlo;
+            if (wi[u] < 0 || wi[u] >= h.wlen) {
+              xg[u] = (col < nloc) ? ld_ro(x + col) : ld_ro(ghost + (col - nloc));
+              wi[u] = -1;
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < PU; ++u) {
+          const int k = k0 + u * nthr;
+          if (k < cnt) prod[k] = vmul(sval[k], wi[u] >= 0 ? xwin[wi[u]] : xg[u]);
+        }
       }
       if (tid == 0) s_nlong = 0;
       __syncwarp();
@@ -833,7 +817,16 @@ static cudaError_t launch_spmv_ttl(const SpmvArgs& a, cudaStream_t st) {
     cudaFuncSetAttribute(spmv_tile_kernel<IdxT, ValT, XT, THREADS, LONG>,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
   }
-  const int grid = a.nblocks;  // one tile per block; blocks are small and many per SM
+  int grid = a.nblocks;  // one tile per block; blocks are small and many per SM
+  if (a.contig) {
+    int occ = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+            &occ, spmv_tile_kernel<IdxT, ValT, XT, THREADS, LONG>, THREADS, smem) != cudaSuccess || occ < 1)
+      occ = 1;
+    if (a.bps > 0 && a.bps < occ) occ = a.bps;
+    const int64_t g = (int64_t)a.num_sms * occ;
+    if (g < grid) grid = (int)g;
+  }
   spmv_tile_kernel<IdxT, ValT, XT, THREADS, LONG><<<grid, THREADS, smem, st>>>(a);
   return cudaGetLastError();
 }
@@ -916,7 +909,7 @@ static cudaError_t launch_spmv_window(const SpmvArgs& a, cudaStream_t st) {
   static PerDeviceOnce once;
   if (once.first_use()) {
     cudaFuncSetAttribute(spmv_window_kernel<IdxT, ValT, XT>,
-                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
   }
   int occ = 1;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmv_window_kernel<IdxT, ValT, XT>, threads,

@@ -243,6 +243,12 @@ int ab200_set_option(ab200_solver *s, const char *key, int64_t value);
  *            caller forms Q = Q1 Q2.
  * work: caller-provided scratch of at least 4 m m + 8 m doubles. */
 int ab200_host_schur(void *zgees_fn, int m, double *t, double *q, double *work);
+/* The same factorisation for an H_m whose imaginary parts are all zero (real operator, real
+ * basis), through dgees + one complex Givens rotation per 2 x 2 block (scipy.linalg.rsf2csf's
+ * construction): a third of the arithmetic.  A valid complex Schur form, NOT the one zgees
+ * returns (order of the diagonal before sorting, phases, rounding): used where the driver
+ * leaves the reference's arithmetic anyway (see `fast_real_schur` in INTEGRATION.md). */
+int ab200_host_schur_real(void *dgees_fn, int m, double *t, double *q);
 int ab200_host_reorder(void *ztrexc_fn, int m, double *t, double *q, const int64_t *perm,
                        double *work);
 

@@ -134,14 +134,16 @@ def test_ortho_matches_reference_goldens(gpu, golden):
 
 @pytest.mark.parametrize("n,c", [(1, 1), (31, 3), (257, 8), (4099, 17), (100003, 40), (20011, 100),
                                  (5000, 128)])
-@pytest.mark.parametrize("kind", ["gs", "gs_fused_regs", "gs_fused_cpasync", "gs_fused_warp", "mgs"])
+@pytest.mark.parametrize("kind", ["gs", "gs_fused_regs", "gs_fused_cpasync", "gs_fused_warp",
+                                  "gs_fused_pipe", "mgs"])
 def test_ortho_vs_oracle_shapes(gpu, n, c, kind):
     """Ragged sizes (n not a multiple of any tile, c = 1..128) against the oracle; every
     CGS2 schedule (two-sweep rounds, fused sweep with register loads / cp.async staging)."""
     import functools
     from arnoldi_b200 import ortho as _o
     dgks_mgs = _o.dgks_mgs
-    variant = {"gs": 1, "gs_fused_regs": 2, "gs_fused_cpasync": 3, "gs_fused_warp": 4}.get(kind, 0)
+    variant = {"gs": 1, "gs_fused_regs": 2, "gs_fused_cpasync": 3, "gs_fused_warp": 4,
+               "gs_fused_pipe": 5}.get(kind, 0)
     dgks_gs = functools.partial(_o.dgks_gs, options={"ortho_variant": variant})
     kind = "mgs" if kind == "mgs" else "gs"
     rng = np.random.default_rng(n * 131 + c)

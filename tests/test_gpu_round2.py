@@ -480,3 +480,43 @@ def test_spmv_window_kernel(gpu, opts):
                     scale = Aabs @ np.abs(x)
                     assert np.all(np.abs(y - ref) <= 1e-13 * scale + 1e-300), (name, algo, opts)
                     np.testing.assert_array_equal(y[short], ref[short], err_msg=f"{name} {algo} {opts}")
+
+
+@pytest.mark.parametrize("real", [True, False])
+def test_fused_sweep_variants_agree_in_expansions(gpu, real):
+    """Every schedule of the CGS2 sweep (two-sweep rounds, fused with register loads, cp.async
+    staging, mbarrier pipeline) builds the same Arnoldi relation, in float64 and complex128
+    storage, on an operator whose DGKS test fires on every step (the fused sweeps' case)."""
+    from arnoldi_b200.matrices import lap2d_rect
+    from arnoldi_b200.solver import DeviceSolver
+    A = lap2d_rect(301, 257)
+    n = A.shape[0]
+    rng = np.random.default_rng(4)
+    v0 = rng.standard_normal(n).astype(np.complex128)
+    v0 /= np.linalg.norm(v0)
+    m = 34
+    out = {}
+    for variant in (1, 2, 3, 5):
+        for fr in ((0, 1) if variant == 5 else (0,)):
+            with DeviceSolver(n, m) as dev:
+                if not real:
+                    dev.set_option("real_mode", 0)
+                dev.set_option("ortho_variant", variant)
+                dev.set_option("fused_r", fr)
+                dev.set_csr(A.indptr, A.indices, A.data)
+                dev.set_columns(0, v0)
+                cols, k, brk = dev.expand(0, m, 1e-8)
+                assert k == m and not brk
+                st = dev.stats()
+                assert st["real_storage"] == (1 if real else 0)
+                if variant != 1:
+                    assert st["ortho_fused_launches"] == m and st["second_rounds"] > m // 2
+                H = np.array(cols)
+                V = dev.get_columns(0, m + 1)
+            out[(variant, fr)] = (H, V)
+    H0, V0 = out[(1, 0)]
+    assert np.abs(V0.conj().T @ V0 - np.eye(m + 1)).max() < 1e-12
+    np.testing.assert_allclose(A @ V0[:, :m], V0 @ H0[:m + 1, :m], rtol=0, atol=1e-12)
+    for key, (H, V) in out.items():
+        np.testing.assert_allclose(H, H0, rtol=0, atol=2e-12, err_msg=str(key))
+        np.testing.assert_allclose(V, V0, rtol=0, atol=2e-11, err_msg=str(key))
