@@ -72,6 +72,7 @@ SIGNATURES = {
     "ab200_comm_connect": (C.c_int, [_P, C.c_int, C.c_int, C.c_char_p, _P]),
     "ab200_set_halo": (C.c_int, [_P, _P, C.c_int64]),
     "ab200_comm_disconnect": (C.c_int, [_P]),
+    "ab200_comm_bench": (C.c_int, [_P, C.c_int, _D]),
     "ab200_halo_export": (C.c_int, [_P, _P]),
     "ab200_halo_connect": (C.c_int, [_P, C.c_char_p, _P, _P, _P]),
     "ab200_set_timing": (C.c_int, [_P, C.c_int]),

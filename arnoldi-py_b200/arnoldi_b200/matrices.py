@@ -74,6 +74,23 @@ def lap2d(N):
     return sp.csr_matrix((vals, cols, indptr.astype(it)), shape=(n, n))
 
 
+def lap2d_rows(N, row0, row1):
+    """Rows [row0, row1) of ``lap2d(N)`` as a ``RowBlock`` (global column ids), without building
+    the rest: what a rank generates for itself when the whole operator would not fit one host
+    (BASELINE config 5: n up to 2e8).  Bit-identical to slicing ``lap2d(N)``."""
+    from .distributed import RowBlock
+    n = N * N
+    idx = np.arange(row0, row1, dtype=np.int64)
+    gi, gj = idx // N, idx % N
+    keep = np.stack([gi > 0, gj > 0, np.ones(idx.shape[0], bool), gj < N - 1, gi < N - 1], axis=1)
+    counts = keep.sum(axis=1)
+    indptr = np.concatenate(([0], np.cumsum(counts)))
+    it = _index_dtype(5 * n, n)
+    cols = np.stack([idx - N, idx - 1, idx, idx + 1, idx + N], axis=1).astype(it)[keep]
+    vals = np.broadcast_to(np.array([-1.0, -1.0, 4.0, -1.0, -1.0]), (idx.shape[0], 5))[keep]
+    return RowBlock(indptr.astype(it), cols, vals, int(row0), (n, n))
+
+
 # ----------------------------------------------------------------------------------------
 # BASELINE config 4: synthetic nonsymmetric CSR with power-law row lengths, generated
 # shard by shard with a counter-based hash so that ANY block of rows can be regenerated
@@ -98,7 +115,7 @@ POWERLAW_TOP = 16          # rows carrying the separated leading eigenvalues
 
 
 def powerlaw_rows(n, row0, row1, *, seed=0, band=4096, far_prob=1.0 / 32.0, lmin=4, lmax=2048,
-                  alpha=1.35, chunk=1 << 20):
+                  alpha=1.35, chunk=1 << 20, top_base=3.0, top_step=0.25):
     """Rows [row0, row1) of the n x n synthetic operator, as a ``RowBlock`` (global columns).
 
     * row length  L_r = clip(floor(lmin * u^(-1/alpha)), lmin, lmax): Pareto, mean ~ 15
@@ -107,8 +124,10 @@ def powerlaw_rows(n, row0, row1, *, seed=0, band=4096, far_prob=1.0 / 32.0, lmin
       band plus a sparse long-range tail.  Columns inside a row are NOT sorted and may repeat
       (scipy's csr_matvec and the device SpMV both sum entries in stored order).
     * off-diagonal values U(-1, 1) * 0.5 / L_r (row sums < 0.5); diagonal 1 + r/n except
-      POWERLAW_TOP rows spread over the matrix whose diagonal is 3.0 + 0.25 i: the wanted
-      largest-real-part eigenvalues are separated, so the solve converges in a few restarts.
+      POWERLAW_TOP rows spread over the matrix whose diagonal is top_base + top_step i: with the
+      defaults (3.0 + 0.25 i) the wanted largest-real-part eigenvalues are well separated and the
+      solve converges in a few restarts; a small top_step clusters them (many restart cycles:
+      the sustained-throughput variant of config 4).
     """
     from .distributed import RowBlock
     s0 = np.uint64(seed) * np.uint64(0x9E3779B97F4A7C15)
@@ -143,7 +162,7 @@ def powerlaw_rows(n, row0, row1, *, seed=0, band=4096, far_prob=1.0 / 32.0, lmin
         is_top = np.isin(rr[diag].astype(np.int64), top_rows)
         if is_top.any():
             which = np.searchsorted(top_rows, rr[diag].astype(np.int64)[is_top])
-            dval[is_top] = 3.0 + 0.25 * which
+            dval[is_top] = top_base + top_step * which
         val[diag] = dval
         idx_parts.append(col.astype(np.int32 if n < 2**31 else np.int64))
         val_parts.append(val)

@@ -189,6 +189,12 @@ class DeviceSolver:
         if getattr(self, "_h", None) is not None and self._h.value:
             _lib.check(self.lib.ab200_comm_disconnect(self._h))
 
+    def comm_bench(self, iters=1000):
+        """Microseconds per in-kernel peer reduction (1-block exchange kernel, back to back)."""
+        us = C.c_double(0.0)
+        _lib.check(self.lib.ab200_comm_bench(self._h, int(iters), C.byref(us)))
+        return us.value
+
     def set_halo(self, ghost_cols):
         g = np.ascontiguousarray(ghost_cols, dtype=np.int64)
         _lib.check(self.lib.ab200_set_halo(self._h, _ptr(g), int(g.shape[0])))

@@ -1270,6 +1270,34 @@ int ab200_comm_connect(ab200_solver* s, int rank, int nranks, const void* blobs,
   return AB200_OK;
 }
 
+// Latency of the in-kernel peer reduction: `iters` back-to-back launches of the 1-block
+// exchange kernel (remote stores of the partial into every peer, system fence, flag, wait for
+// the peers' flags, rank-order sum), timed with CUDA events on the solver's stream.  Collective:
+// every rank must call it with the same `iters`.
+int ab200_comm_bench(ab200_solver* s, int iters, double* us_per_exchange) {
+  REQUIRE(s != nullptr && us_per_exchange != nullptr && iters >= 1, "bad argument");
+  if (s->nranks <= 1) return set_err(AB200_ESTATE, "ab200_comm_bench needs ab200_comm_connect first");
+  if (s->disconnected) return set_err(AB200_ESTATE, "ab200_comm_bench after ab200_comm_disconnect");
+  CU(cudaSetDevice(s->device));
+  init_ctl_kernel<<<1, 32, 0, s->stream>>>(s->ctl, nullptr, 0, false);
+  for (int i = 0; i < 8; ++i) CU(launch_peer_barrier(s->comm, s->ctl, s->real_mode ? 1 : 0, s->stream));
+  cudaEvent_t a, b;
+  CU(cudaEventCreate(&a));
+  CU(cudaEventCreate(&b));
+  CU(cudaEventRecord(a, s->stream));
+  for (int i = 0; i < iters; ++i) CU(launch_peer_barrier(s->comm, s->ctl, s->real_mode ? 1 : 0, s->stream));
+  CU(cudaEventRecord(b, s->stream));
+  CU(cudaEventSynchronize(b));
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, a, b));
+  cudaEventDestroy(a), cudaEventDestroy(b);
+  CU(cudaMemcpy(s->h_ctl, s->ctl, sizeof(StepCtl), cudaMemcpyDeviceToHost));
+  if (s->h_ctl->comm_error) return set_err(AB200_ECOMM, "peer reduction timed out");
+  s->st.kernel_launches += iters + 9;
+  *us_per_exchange = 1e3 * (double)ms / iters;
+  return AB200_OK;
+}
+
 int ab200_set_halo(ab200_solver* s, const int64_t* ghost_cols, int64_t nghost) {
   REQUIRE(s != nullptr && nghost >= 0 && (nghost == 0 || ghost_cols != nullptr), "bad argument");
   if (nghost > 0 && s->nranks <= 1)

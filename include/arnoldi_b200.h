@@ -190,6 +190,9 @@ int ab200_set_halo(ab200_solver *s, const int64_t *ghost_cols, int64_t nghost);
  * calls it, the ranks meet (host barrier), then each calls ab200_destroy -- so no rank frees
  * memory a peer still maps or reads.  The handle accepts no further multi-GPU work. */
 int ab200_comm_disconnect(ab200_solver *s);
+/* Measure the fused peer reduction alone: `iters` back-to-back 1-block exchanges (launch + remote
+ * stores + system fence + flags + rank-order sum), microseconds per exchange.  Collective. */
+int ab200_comm_bench(ab200_solver *s, int iters, double *us_per_exchange);
 /* Optional owner-side push of the halo (for scattered halos).  After ab200_set_halo on every
  * rank: ab200_halo_export writes a blob with the IPC handles of this rank's ghost buffer and
  * delivery flags; ab200_halo_connect takes all ranks' blobs plus, for every peer r, the LOCAL

@@ -29,6 +29,10 @@ def main():
     ap.add_argument("--max-restarts", type=int, default=100000)
     ap.add_argument("--ortho", default="cgs2")
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--real-arith", default="lossless", choices=["lossless", "pairs", "off"])
+    ap.add_argument("--fast-real-schur", action="store_true")
+    ap.add_argument("--dynamic-p", action="store_true")
+    ap.add_argument("--lock", action="store_true")
     args = ap.parse_args()
 
     from arnoldi_b200 import matrices, partial_schur
@@ -40,14 +44,19 @@ def main():
     t0 = time.perf_counter()
     Q, T, hist = partial_schur(A, args.nev, max_dim=args.max_dim, stopping_criterion=args.tol,
                                max_restarts=args.max_restarts, sort_function=arg_largest_real,
-                               ortho=args.ortho, stats=stats)
+                               ortho=args.ortho, stats=stats, real_arith=args.real_arith,
+                               fast_real_schur=args.fast_real_schur, dynamic_p=args.dynamic_p,
+                               lock=args.lock)
     dt = time.perf_counter() - t0
     w, S = np.linalg.eig(T)
     X = Q @ S
     res = np.linalg.norm(A @ X - X * w, axis=0) / np.abs(w)
     out = {
         "config": f"{args.matrix}({args.grid}) n={n} nnz={A.nnz} K={args.nev} max_dim={args.max_dim} "
-                  f"LR tol={args.tol} seed={args.seed} ortho={args.ortho}",
+                  f"LR tol={args.tol} seed={args.seed} ortho={args.ortho} real_arith={args.real_arith} "
+                  f"fast_real_schur={args.fast_real_schur} dynamic_p={args.dynamic_p} lock={args.lock}",
+        "pairs_kept_whole": int(stats.get("pairs_kept_whole", 0)),
+        "real_storage_at_end": int(stats.get("real_storage", 0)),
         "time_to_k_converged_s": dt, "restarts": int(hist.restarts[0]),
         "history_matvecs": int(hist.matvecs[0]), "true_matvecs": int(stats["true_matvecs"]),
         "matvecs_per_s": stats["true_matvecs"] / dt,

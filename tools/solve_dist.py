@@ -28,6 +28,13 @@ def main():
     ap.add_argument("--tol", type=float, default=1e-8)
     ap.add_argument("--max-restarts", type=int, default=100000)
     ap.add_argument("--ortho", default="cgs2")
+    ap.add_argument("--real-arith", default="lossless", choices=["lossless", "pairs", "off"])
+    ap.add_argument("--fast-real-schur", action="store_true")
+    ap.add_argument("--top-base", type=float, default=3.0)
+    ap.add_argument("--top-step", type=float, default=0.25,
+                    help="powerlaw: spacing of the leading diagonal entries (0.01 with --top-base 2 "
+                         "clusters them: ~60 restart cycles instead of 1)")
+    ap.add_argument("--spmv-algo", default="auto")
     args = ap.parse_args()
 
     import torch
@@ -46,7 +53,7 @@ def main():
         n = args.rows
         part = RowPartition(n, world)
         r0, r1 = part.rows(rank)
-        A = matrices.powerlaw_rows(n, r0, r1)          # this rank's rows only
+        A = matrices.powerlaw_rows(n, r0, r1, top_base=args.top_base, top_step=args.top_step)
         nnz_local = int(A.indptr[-1])
     else:
         M = getattr(matrices, args.matrix)(args.grid)
@@ -62,7 +69,9 @@ def main():
     t0 = time.perf_counter()
     Q, T, hist = partial_schur(A, args.nev, max_dim=args.max_dim, stopping_criterion=args.tol,
                                max_restarts=args.max_restarts, sort_function=arg_largest_real,
-                               ortho=args.ortho, device=local, comm=comm, stats=stats)
+                               ortho=args.ortho, device=local, comm=comm, stats=stats,
+                               real_arith=args.real_arith, fast_real_schur=args.fast_real_schur,
+                               spmv_algo=args.spmv_algo)
     dt = comm.max_float(time.perf_counter() - t0)
     # true residual ||A Q - Q T|| needs A applied to the sharded Q: done with the local block
     # and an all-gather of Q (nev columns)
@@ -77,7 +86,9 @@ def main():
     if rank == 0:
         out = {
             "config": f"{args.matrix} n={n} nnz={nnz} K={args.nev} max_dim={args.max_dim} LR "
-                      f"tol={args.tol} seed=0 ortho={args.ortho} world={world}",
+                      f"tol={args.tol} seed=0 ortho={args.ortho} world={world} real_arith={args.real_arith} "
+                      f"fast_real_schur={args.fast_real_schur} top=({args.top_base},{args.top_step})",
+            "pairs_kept_whole": int(stats.get("pairs_kept_whole", 0)),
             "generate_s_rank0": round(t_gen, 2), "time_to_k_converged_s": dt,
             "restarts": int(hist.restarts[0]), "true_matvecs": int(stats["true_matvecs"]),
             "matvecs_per_s": stats["true_matvecs"] / dt,
