@@ -72,10 +72,12 @@ struct SpmvArgs {
   int stages;              // shared-memory ring depth
   int rp_cap;              // row pointers staged per tile (multiple of 4)
   int bps;                 // resident blocks per SM to launch (0 = what fits)
-  // skewed rows with local columns (spmv_window_kernel): x entries of the tile's window that
-  // are staged in shared memory
-  int window;
-  int win_cap;
+  // skewed rows with local columns (spmv_ring_kernel): the x entries around the diagonal live in
+  // a shared-memory ring
+  int window;              // use the ring kernel
+  int win_cap;             // ring capacity in float64 entries (power of two; complex: half as many)
+  int win_half;            // entries kept on each side of a round's rows
+  int ring_warps;          // consumer warps per block
   int contig;              // tile kernel: persistent blocks over contiguous tile ranges (L1 reuse of x)
   // halo read straight from the owners' HBM (multi-GPU "pull"): ghost entry g of rank q lives at
   // peer_col[q][ghost_off[g]]; entries [seg_start[q], seg_start[q+1]) belong to rank q
@@ -87,7 +89,7 @@ struct SpmvArgs {
 };
 
 cudaError_t launch_spmv(const SpmvArgs& a, int indptr_bits, int value_kind, cudaStream_t st);
-size_t spmv_window_smem(int win_cap, int rp_cap, int val_bytes, int idx_bytes, int x_bytes);
+size_t spmv_ring_smem(int win_cap, int nwarps, int x_bytes);
 // fraction (in 1/1024ths, over a sample of the rows) of the entries whose column lies within
 // `half` of their row: decides whether staging an x window in shared memory pays
 cudaError_t launch_spmv_locality(const void* indptr, int indptr_bits, const int32_t* indices, int64_t n,

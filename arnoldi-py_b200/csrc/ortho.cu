@@ -34,6 +34,25 @@ __device__ __forceinline__ double sum_partials(const double* part, int nblocks, 
 
 // Cross-GPU sum of `count` doubles held in red[] (local result), in rank order.
 // Called by every thread of the last block; returns with red[] = global sums.
+//
+// One NVLink trip, no flag round: every double travels as two 8-byte packets
+// {32 data bits, 32-bit sequence number}, each written with ONE 64-bit store into slot[my rank]
+// of every rank.  An aligned 64-bit store is single-copy atomic, so a reader that sees the
+// sequence number sees the data that came with it: no fence between payload and flag, no wait
+// for the remote stores to be acknowledged (the first version pushed the payload, fenced at
+// system scope -- one NVLink round trip -- and only then raised a flag).  Slots alternate with
+// the parity of the sequence number, so a packet of exchange seq can only be overwritten by
+// exchange seq + 2, which no rank starts before every rank has finished reading seq.
+// The system-scope fence BEFORE the stores keeps the release semantics the halo reads rely on:
+// whoever receives this rank's packets also sees every basis entry this rank wrote before.
+__device__ __forceinline__ void st_packet(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_packet(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ void peer_allreduce(const PeerComm& pc, double* red, int count, StepCtl* ctl) {
   if (pc.nranks <= 1) return;
   __shared__ unsigned long long s_seq;
@@ -41,45 +60,51 @@ __device__ void peer_allreduce(const PeerComm& pc, double* red, int count, StepC
   if (tid == 0) s_seq = *pc.seq + 1ull;
   __syncthreads();
   const unsigned long long seq = s_seq;
+  const unsigned long long tag = (seq & 0xffffffffull) << 32;
   const int par = (int)(seq & 1ull);
-  const size_t slot_off = ((size_t)par * kMaxRanks + pc.rank) * pc.slot_doubles;
-  // 1. push my partial into slot[my rank] of every rank (mine included)
-  for (int r = 0; r < pc.nranks; ++r) {
-    double* dst = pc.slots[r] + slot_off;
-    for (int k = tid; k < count; k += blockDim.x) dst[k] = red[k];
-  }
-  __threadfence_system();
-  __syncthreads();
-  // 2. raise my flag on every rank
-  if (tid < pc.nranks) {
-    volatile unsigned long long* f = pc.flags[tid] + (size_t)par * kMaxRanks + pc.rank;
-    *f = seq;
-  }
-  // 3. wait for every rank's flag in my own flag array (wall-clock bound: a peer that died or
-  //    diverged must not hang the box; on timeout every later kernel becomes a no-op)
-  if (tid < pc.nranks) {
-    volatile unsigned long long* f = pc.flags[pc.rank] + (size_t)par * kMaxRanks + tid;
-    const unsigned long long t0 = global_ns();
-    unsigned spins = 0;
-    while (*f < seq) {
-      if ((++spins & 0x3ffu) == 0 && global_ns() - t0 > kPeerTimeoutNs) {
-        ctl->comm_error = 1;
-        ctl->stop = 1;
-        break;
-      }
+  __threadfence_system();   // release: this rank's basis writes precede its packets
+  // 1. my partial into slot[my rank] of every rank (mine included)
+  const size_t my_off = 2 * ((size_t)par * kMaxRanks + pc.rank) * pc.slot_doubles;
+  for (int k = tid; k < count; k += blockDim.x) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(red[k]);
+    const unsigned long long lo = tag | (bits & 0xffffffffull), hi = tag | (bits >> 32);
+    for (int r = 0; r < pc.nranks; ++r) {
+      unsigned long long* dst = reinterpret_cast<unsigned long long*>(pc.slots[r]) + my_off + 2 * (size_t)k;
+      st_packet(dst, lo);
+      st_packet(dst + 1, hi);
     }
   }
-  __syncthreads();
-  __threadfence_system();
-  // 4. sum in rank order
-  const double* mine = pc.slots[pc.rank] + (size_t)par * kMaxRanks * pc.slot_doubles;
+  __syncthreads();   // red[] has been read by everyone before it is overwritten below
+  // 2. collect: wait for both packets of every rank's k-th double, sum in rank order
+  //    (wall-clock bound: a peer that died or diverged must not hang the box; on timeout every
+  //    later kernel becomes a no-op)
+  const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(pc.slots[pc.rank]) +
+                                   2 * (size_t)par * kMaxRanks * pc.slot_doubles;
+  const unsigned long long t0 = global_ns();
+  bool dead = false;
   for (int k = tid; k < count; k += blockDim.x) {
     double a = 0.0;
-    for (int r = 0; r < pc.nranks; ++r)
-      a += *((volatile const double*)(mine + (size_t)r * pc.slot_doubles + k));
+    for (int r = 0; r < pc.nranks; ++r) {
+      const unsigned long long* src = mine + 2 * ((size_t)r * pc.slot_doubles + k);
+      unsigned long long lo, hi;
+      unsigned spins = 0;
+      for (;;) {
+        lo = ld_packet(src);
+        hi = ld_packet(src + 1);
+        if (((lo ^ tag) >> 32) == 0 && ((hi ^ tag) >> 32) == 0) break;
+        if (dead || ((++spins & 0x3ffu) == 0 && global_ns() - t0 > kPeerTimeoutNs)) {
+          dead = true;
+          ctl->comm_error = 1;
+          ctl->stop = 1;
+          break;
+        }
+      }
+      a += __longlong_as_double((long long)((hi << 32) | (lo & 0xffffffffull)));
+    }
     red[k] = a;
   }
   __syncthreads();
+  __threadfence_system();   // acquire: later reads of peer memory see what the senders released
   if (tid == 0) *pc.seq = seq;
 }
 

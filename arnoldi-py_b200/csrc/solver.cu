@@ -51,6 +51,8 @@ struct TimedLaunch {
   int round;  // 1, 2 or 0
   double bytes;
   cudaEvent_t a, b;
+  bool a_shared;   // `a` is the end event of the launch enqueued just before (not owned)
+  int executed;    // -1 until the expansion's flags are known
 };
 
 struct ab200_solver {
@@ -95,7 +97,7 @@ struct ab200_solver {
   int spmv_threads = 128;
   int spmv_algo = AB200_SPMV_AUTO;
   int spmv_stages = 3, spmv_rp_cap = 0;
-  int spmv_window = 0, spmv_win_cap = 0;   // skewed rows with local columns: x window in smem
+  int spmv_window = 0, spmv_win_cap = 0, spmv_win_half = 0;   // skewed rows: x ring in smem
   int spmv_locality_pm = 0;                // per-mille of sampled entries within the window
   int max_row_len = 0;
   // user-supplied device operator (ab200_set_operator) instead of a CSR block
@@ -108,7 +110,7 @@ struct ab200_solver {
   // multi-GPU state
   int rank = 0, nranks = 1;
   int64_t row_starts[kMaxRanks + 1] = {0};
-  double* slots = nullptr;                 // my receive area: [2][kMaxRanks][slot_doubles]
+  double* slots = nullptr;                 // my receive area: [2][kMaxRanks][slot_doubles] x 2 packets
   unsigned long long* flags = nullptr;     // my flags: [2][kMaxRanks]
   unsigned long long* seq = nullptr;       // exchange counter
   void* peer_V[kMaxRanks] = {nullptr};     // IPC mappings (nullptr for self / unused)
@@ -132,7 +134,8 @@ struct ab200_solver {
   // options
   int opt_grid_mult = 0, opt_restart_variant = 0, opt_ortho_variant = 0, opt_spmv_tile = 0,
       opt_fused_ct = 0, opt_spmv_threads = 0, opt_fused_stages = 0, opt_fused_r = 0, opt_spmv_variant = 0,
-      opt_spmv_stages = 0, opt_spmv_bps = 0, opt_halo_fold = 1, opt_spmv_window = 0;
+      opt_spmv_stages = 0, opt_spmv_bps = 0, opt_halo_fold = 1, opt_spmv_window = 0,
+      opt_spmv_win_half = 0, opt_spmv_ring_warps = 0;
   bool disconnected = false;
   // download path: two pinned bounce buffers + a copy stream (ab200_get_columns)
   void* bounce[2] = {nullptr, nullptr};
@@ -154,6 +157,7 @@ struct ab200_solver {
   // identical real parts).  The first complex input converts it in place, once.
   bool real_mode = true;
   bool pristine = true;   // no column has been written yet
+  cudaEvent_t chain_event = nullptr;   // end event of the launch enqueued last, while nothing followed it
 };
 
 static cudaEvent_t get_event(ab200_solver* s) {
@@ -177,32 +181,55 @@ struct LaunchScope {
     t.step = step;
     t.round = round;
     t.bytes = bytes;
+    t.a_shared = false;
+    t.executed = -1;
     if (on) {
-      t.a = get_event(s);
+      // consecutive launches share their boundary event: one record per launch instead of two
+      // (event records sit on the stream between the kernels: ~3 us each at this kernel size)
+      if (s->chain_event != nullptr) {
+        t.a = s->chain_event;
+        t.a_shared = true;
+      } else {
+        t.a = get_event(s);
+        cudaEventRecord(t.a, s->stream);
+      }
       t.b = get_event(s);
-      cudaEventRecord(t.a, s->stream);
     } else {
       t.a = t.b = nullptr;
     }
   }
   ~LaunchScope() {
-    if (on) cudaEventRecord(t.b, s->stream);
+    if (on) {
+      cudaEventRecord(t.b, s->stream);
+      s->chain_event = t.b;
+    }
     s->pending.push_back(t);
     s->st.kernel_launches += 1;
   }
 };
+// anything enqueued outside a LaunchScope ends the chain of shared boundary events
+static inline void break_chain(ab200_solver* s) { s->chain_event = nullptr; }
 
-// fold pending launches into the stats; the stream must be idle
-static void resolve_pending(ab200_solver* s, const int* step_round2 /* may be null */) {
+// Mark which pending launches really ran (needs the expansion's flags: cheap, no CUDA call) and,
+// when `flush` or the backlog is large, read their event times and fold them into the stats.
+// The stream must be idle.
+static void resolve_pending(ab200_solver* s, const int* step_round2 /* may be null */, bool flush = false) {
+  break_chain(s);
   for (auto& t : s->pending) {
+    if (t.executed >= 0) continue;
     bool executed = true;
     if (t.round == 2 && t.step >= 0 && step_round2 != nullptr && !step_round2[t.step])
       executed = false;
     if (t.step >= 0 && s->h_ctl && s->h_ctl->stop && t.step > s->h_ctl->broke_at) executed = false;
+    t.executed = executed ? 1 : 0;
+  }
+  if (!flush && s->pending.size() < 4096) return;
+  for (auto& t : s->pending) {
+    const bool executed = t.executed != 0;
     float ms = 0.f;
     if (t.a) {
       cudaEventElapsedTime(&ms, t.a, t.b);
-      s->pool.push_back(t.a);
+      if (!t.a_shared) s->pool.push_back(t.a);
       s->pool.push_back(t.b);
     }
     if (!executed) continue;
@@ -384,6 +411,7 @@ int ab200_device_count(void) {
 int ab200_comm_disconnect(ab200_solver* s) {
   REQUIRE(s != nullptr, "solver is null");
   CU(cudaSetDevice(s->device));
+  break_chain(s);
   if (s->stream) CU(cudaStreamSynchronize(s->stream));
   for (int r = 0; r < kMaxRanks; ++r) {
     if (s->peer_V[r]) cudaIpcCloseMemHandle(s->peer_V[r]);
@@ -401,7 +429,7 @@ int ab200_destroy(ab200_solver* s) {
   if (!s) return AB200_OK;
   cudaSetDevice(s->device);
   if (s->stream) cudaStreamSynchronize(s->stream);
-  resolve_pending(s, nullptr);
+  resolve_pending(s, nullptr, true);
   for (auto e : s->pool) cudaEventDestroy(e);
   if (s->t0) cudaEventDestroy(s->t0), cudaEventDestroy(s->t1);
   // imports first (a no-op after ab200_comm_disconnect), then the buffers this rank owns
@@ -521,6 +549,7 @@ int ab200_set_csr(ab200_solver* s, const void* indptr, int indptr_bits, const in
   REQUIRE(first == 0 && last == nnz, "indptr[0]=%lld, indptr[n]=%lld, nnz=%lld: not a CSR block",
           (long long)first, (long long)last, (long long)nnz);
   CU(cudaSetDevice(s->device));
+  break_chain(s);
   CU(cudaStreamSynchronize(s->stream));
   if (value_kind == AB200_C128) {
     int rc = switch_to_complex(s);
@@ -572,37 +601,45 @@ int ab200_set_csr(ab200_solver* s, const void* indptr, int indptr_bits, const in
     if (tile > 4096) tile = 4096;
     if (!short_rows && tile > 1280) tile = 1280;  // skewed rows: measured best on the power-law operator
   }
-  // Skewed rows: stage the x window of each tile in shared memory when most entries sit near
-  // the diagonal (sampled on the device); AB200_SPMV_MERGE asks for it regardless.
+  // Skewed rows: gather x from a shared-memory ring that slides along the diagonal
+  // (spmv_ring_kernel) when most entries sit near the diagonal -- sampled on the device.
+  // AB200_SPMV_MERGE asks for it regardless; AB200_SPMV_VECTOR keeps the plain tile kernel.
   s->spmv_window = 0;
   s->spmv_locality_pm = 0;
   if (!short_rows && spmv_algo != AB200_SPMV_VECTOR && nnz > 0) {
-    const int want = s->opt_spmv_window > 0 ? s->opt_spmv_window : 8704;  // +-4096 and the tile's rows
+    // ring capacity in x entries.  8192 (64 KB) measured best on the power-law operator: it holds
+    // +-3328 entries around a round's rows and leaves ~90 KB of L1 to the gathers that miss it
+    // (16384 entries: 1.00 ms, 8192: 0.92 ms at n = 1e7)
+    int wcap = s->opt_spmv_window > 0 ? s->opt_spmv_window : 8192;
+    if (wcap < 256) wcap = 256;
+    if (wcap > 16384) wcap = 16384;
+    wcap = wcap / 256 * 256;
+    // entries kept on each side of a round's rows; the rest of the ring lets the warps drift apart
+    const int half = s->opt_spmv_win_half > 0 ? s->opt_spmv_win_half : (wcap >= 12288 ? 4608 : (wcap - 1536) / 2);
     unsigned long long* cnt = nullptr;
     CU(cudaMalloc(&cnt, 2 * sizeof(unsigned long long)));
     CU(cudaMemsetAsync(cnt, 0, 2 * sizeof(unsigned long long), s->stream));
-    CU(launch_spmv_locality(s->indptr, indptr_bits, s->indices, s->n, s->n_local_cols, (want - 512) / 2,
-                            cnt, s->stream));
+    CU(launch_spmv_locality(s->indptr, indptr_bits, s->indices, s->n, s->n_local_cols, half, cnt,
+                            s->stream));
     unsigned long long h[2] = {0, 0};
     CU(cudaMemcpyAsync(h, cnt, sizeof(h), cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     cudaFree(cnt);
     s->spmv_locality_pm = h[1] ? (int)(1000.0 * (double)h[0] / (double)h[1]) : 0;
-    // measured (powerlaw n = 1e7, real storage): the window kernel reaches 1.3-1.6 TB/s against
-    // 1.7 TB/s for the tile kernel (its tiles serialise on the window load and on the far
-    // gathers), so AUTO keeps the tile kernel; AB200_SPMV_MERGE selects the window kernel
-    if (spmv_algo == AB200_SPMV_MERGE) {
+    if (spmv_algo == AB200_SPMV_MERGE || s->spmv_locality_pm >= 500) {
       s->spmv_window = 1;
-      s->spmv_win_cap = (want + 15) / 16 * 16;
-      if (s->opt_spmv_tile <= 0) tile = 4096;
+      s->spmv_win_cap = wcap;
+      s->spmv_win_half = half;
+      if (s->opt_spmv_tile <= 0) tile = 512;   // one tile = one warp's strip of products
     }
   }
+  if (tile > 8192) tile = 8192;   // 8192 complex entries + column ids = 164 KB of shared memory
   tile = (tile + 7) / 8 * 8;
   s->spmv_threads = threads;
   // measured on lap2d(4096) / mark(4000): two stages of one-row-per-thread tiles are enough
   // (6.47 TB/s; 3 stages 6.30, 4 stages 5.83 -- deeper rings only take L1 away from the gathers)
   s->spmv_stages = s->opt_spmv_stages >= 2 && s->opt_spmv_stages <= 8 ? s->opt_spmv_stages : 2;
-  s->spmv_rp_cap = s->spmv_window ? 1032 : 2 * threads + 8;
+  s->spmv_rp_cap = 2 * threads + 8;
   int64_t nblk = (nnz + tile - 1) / tile;
   if (nblk < 1) nblk = 1;
   REQUIRE(nblk < (1ll << 30), "too many SpMV tiles");
@@ -626,6 +663,7 @@ int ab200_set_operator(ab200_solver* s, ab200_apply_fn fn, void* user, int value
   REQUIRE(value_kind == AB200_F64 || value_kind == AB200_C128, "bad value_kind %d", value_kind);
   if (s->nranks > 1) return set_err(AB200_ESTATE, "device operators are single-GPU");
   CU(cudaSetDevice(s->device));
+  break_chain(s);
   CU(cudaStreamSynchronize(s->stream));
   if (value_kind == AB200_C128) {
     int rc = switch_to_complex(s);
@@ -645,6 +683,7 @@ int ab200_set_columns(ab200_solver* s, int col0, int ncols, const double* host, 
           col0, col0 + ncols, s->max_dim + 1);
   REQUIRE(ld_host >= s->n, "ld_host < nrows_local");
   CU(cudaSetDevice(s->device));
+  break_chain(s);
   if (s->real_mode) {
     // stay real only if every imaginary part is exactly zero
     bool all_real = true;
@@ -744,6 +783,7 @@ int ab200_get_columns(ab200_solver* s, int col0, int ncols, double* host, int64_
           col0, col0 + ncols, s->max_dim + 1);
   REQUIRE(ld_host >= s->n, "ld_host < nrows_local");
   CU(cudaSetDevice(s->device));
+  break_chain(s);
   char* out = reinterpret_cast<char*>(host);
   if (s->real_mode) {
     // expand column by column through the scratch vector, lazy scale applied on the way out
@@ -814,6 +854,8 @@ static int enqueue_spmv(ab200_solver* s, const void* x, void* y, const double* x
   a.window = s->spmv_window && s->opt_spmv_variant == 0;
   a.contig = s->opt_spmv_variant == 3 ? 1 : 0;
   a.win_cap = s->spmv_win_cap;
+  a.win_half = s->spmv_win_half;
+  a.ring_warps = s->opt_spmv_ring_warps > 0 ? s->opt_spmv_ring_warps : 15;
   const double sv = s->value_kind == AB200_F64 ? 8.0 : 16.0;
   const double eb = a.real ? 8.0 : 16.0;
   const double bytes = (double)s->nnz * (sv + 4.0) + (double)s->n * (s->indptr_bits / 8 + 2.0 * eb) +
@@ -894,6 +936,7 @@ int ab200_expand(ab200_solver* s, int start_dim, int end_dim, double tol, double
     return set_err(AB200_ESTATE, "ab200_expand called before ab200_set_csr / ab200_set_operator");
   if (s->disconnected) return set_err(AB200_ESTATE, "ab200_expand after ab200_comm_disconnect");
   CU(cudaSetDevice(s->device));
+  break_chain(s);
   s->pristine = false;
   const int md1 = s->max_dim + 1;
   init_ctl_kernel<<<1, 32, 0, s->stream>>>(s->ctl, nullptr, 0, false);
@@ -957,6 +1000,7 @@ int ab200_expand(ab200_solver* s, int start_dim, int end_dim, double tol, double
 static int apply_q(ab200_solver* s, const double* q, int64_t ldq, int col0, int m, int p,
                    bool copy_tail) {
   CU(cudaSetDevice(s->device));
+  break_chain(s);
   CU(cudaStreamSynchronize(s->stream));  // the pinned Q staging buffer is free again
   const cplx* qh = reinterpret_cast<const cplx*>(q);
   if (s->real_mode) {
@@ -1041,6 +1085,7 @@ int ab200_orthonormalize_column(ab200_solver* s, int col, int ncols, double tol,
   if (s->disconnected)
     return set_err(AB200_ESTATE, "ab200_orthonormalize_column after ab200_comm_disconnect");
   CU(cudaSetDevice(s->device));
+  break_chain(s);
   s->pristine = false;
   init_ctl_kernel<<<1, 32, 0, s->stream>>>(s->ctl, nullptr, 0, false);
   CU(cudaGetLastError());
@@ -1090,6 +1135,7 @@ int ab200_project(ab200_solver* s, int col, int nrows, double* h_host) {
   if (s->nnz < 0) return set_err(AB200_ESTATE, "ab200_project called before an operator was set");
   if (s->disconnected) return set_err(AB200_ESTATE, "ab200_project after ab200_comm_disconnect");
   CU(cudaSetDevice(s->device));
+  break_chain(s);
   init_ctl_kernel<<<1, 32, 0, s->stream>>>(s->ctl, nullptr, 0, false);
   CU(cudaGetLastError());
   s->st.kernel_launches += 1;
@@ -1123,6 +1169,7 @@ int ab200_spmv(ab200_solver* s, const double* x_host, double* y_host) {
   if (s->n != s->n_global)
     return set_err(AB200_ESTATE, "ab200_spmv is a single-GPU entry point (row block is partial)");
   CU(cudaSetDevice(s->device));
+  break_chain(s);
   if (!s->xtmp) CU(cudaMalloc(&s->xtmp, sizeof(cplx) * (size_t)s->ld));
   // a real x on a real operator takes the float64 kernels, exactly as inside a real-storage
   // expansion (the complex result has zero imaginary parts either way)
@@ -1163,6 +1210,7 @@ int ab200_ortho(ab200_solver* s, int ncols, double* w_host, double* h_host, doub
           ortho_kind);
   if (s->disconnected) return set_err(AB200_ESTATE, "ab200_ortho after ab200_comm_disconnect");
   CU(cudaSetDevice(s->device));
+  break_chain(s);
   {  // the stand-alone plug takes an arbitrary complex w: work on complex storage
     int rc = switch_to_complex(s);
     if (rc != AB200_OK) return rc;
@@ -1207,11 +1255,13 @@ static const int kSlotDoubles = 2 * 129 + 8;
 int ab200_comm_export(ab200_solver* s, void* blob) {
   REQUIRE(s != nullptr && blob != nullptr, "null argument");
   CU(cudaSetDevice(s->device));
+  break_chain(s);
   if (!s->slots) {
-    CU(cudaMalloc(&s->slots, sizeof(double) * 2 * kMaxRanks * kSlotDoubles));
+    // two 8-byte packets per double (peer_allreduce)
+    CU(cudaMalloc(&s->slots, 2 * sizeof(double) * 2 * kMaxRanks * kSlotDoubles));
     CU(cudaMalloc(&s->flags, sizeof(unsigned long long) * 2 * kMaxRanks));
     CU(cudaMalloc(&s->seq, sizeof(unsigned long long)));
-    CU(cudaMemset(s->slots, 0, sizeof(double) * 2 * kMaxRanks * kSlotDoubles));
+    CU(cudaMemset(s->slots, 0, 2 * sizeof(double) * 2 * kMaxRanks * kSlotDoubles));
     CU(cudaMemset(s->flags, 0, sizeof(unsigned long long) * 2 * kMaxRanks));
     CU(cudaMemset(s->seq, 0, sizeof(unsigned long long)));
     CU(cudaDeviceSynchronize());
@@ -1240,6 +1290,7 @@ int ab200_comm_connect(ab200_solver* s, int rank, int nranks, const void* blobs,
   REQUIRE(row_starts[rank] == s->row0 && row_starts[rank + 1] == s->row0 + s->n,
           "row_starts[rank] does not match this solver's row block");
   CU(cudaSetDevice(s->device));
+  break_chain(s);
   const unsigned char* bl = static_cast<const unsigned char*>(blobs);
   for (int r = 0; r < nranks; ++r) {
     CommBlob b;
@@ -1279,6 +1330,7 @@ int ab200_comm_bench(ab200_solver* s, int iters, double* us_per_exchange) {
   if (s->nranks <= 1) return set_err(AB200_ESTATE, "ab200_comm_bench needs ab200_comm_connect first");
   if (s->disconnected) return set_err(AB200_ESTATE, "ab200_comm_bench after ab200_comm_disconnect");
   CU(cudaSetDevice(s->device));
+  break_chain(s);
   init_ctl_kernel<<<1, 32, 0, s->stream>>>(s->ctl, nullptr, 0, false);
   for (int i = 0; i < 8; ++i) CU(launch_peer_barrier(s->comm, s->ctl, s->real_mode ? 1 : 0, s->stream));
   cudaEvent_t a, b;
@@ -1303,6 +1355,7 @@ int ab200_set_halo(ab200_solver* s, const int64_t* ghost_cols, int64_t nghost) {
   if (nghost > 0 && s->nranks <= 1)
     return set_err(AB200_ESTATE, "ab200_set_halo with ghost columns needs ab200_comm_connect first");
   CU(cudaSetDevice(s->device));
+  break_chain(s);
   CU(cudaStreamSynchronize(s->stream));
   cudaFree(s->ghost), cudaFree(s->ghost_off);
   s->ghost = nullptr, s->ghost_off = nullptr, s->nghost = 0;
@@ -1342,6 +1395,7 @@ int ab200_halo_export(ab200_solver* s, void* blob) {
   REQUIRE(s != nullptr && blob != nullptr, "null argument");
   if (s->nranks <= 1) return set_err(AB200_ESTATE, "ab200_halo_export needs ab200_comm_connect first");
   CU(cudaSetDevice(s->device));
+  break_chain(s);
   if (!s->hflags) {
     CU(cudaMalloc(&s->hflags, sizeof(unsigned long long) * kMaxRanks));
     CU(cudaMemset(s->hflags, 0, sizeof(unsigned long long) * kMaxRanks));
@@ -1369,6 +1423,7 @@ int ab200_halo_connect(ab200_solver* s, const void* blobs, const int64_t* send_i
           "null argument");
   if (!s->hflags) return set_err(AB200_ESTATE, "ab200_halo_connect before ab200_halo_export");
   CU(cudaSetDevice(s->device));
+  break_chain(s);
   const unsigned char* bl = static_cast<const unsigned char*>(blobs);
   REQUIRE(send_ptr[0] == 0, "send_ptr[0] must be 0");
   for (int r = 0; r < s->nranks; ++r) {
@@ -1410,8 +1465,9 @@ int ab200_set_timing(ab200_solver* s, int enabled) {
 int ab200_reset_stats(ab200_solver* s) {
   REQUIRE(s != nullptr, "solver is null");
   CU(cudaSetDevice(s->device));
+  break_chain(s);
   CU(cudaStreamSynchronize(s->stream));
-  resolve_pending(s, nullptr);
+  resolve_pending(s, nullptr, true);
   memset(&s->st, 0, sizeof(s->st));
   init_ctl_kernel<<<1, 32, 0, s->stream>>>(s->ctl, nullptr, 0, true);
   CU(cudaGetLastError());
@@ -1421,10 +1477,11 @@ int ab200_reset_stats(ab200_solver* s) {
 
 int ab200_get_stats(ab200_solver* s, ab200_stats* out) {
   REQUIRE(s != nullptr && out != nullptr, "null argument");
-  if (!s->pending.empty()) {  // e.g. a restart update enqueued after the last expansion
+  if (!s->pending.empty()) {  // launches whose event times have not been read yet
     CU(cudaSetDevice(s->device));
+    break_chain(s);
     CU(cudaStreamSynchronize(s->stream));
-    resolve_pending(s, s->h_step_round2);
+    resolve_pending(s, s->h_step_round2, true);
   }
   *out = s->st;
   out->real_storage = s->real_mode ? 1 : 0;
@@ -1434,6 +1491,7 @@ int ab200_get_stats(ab200_solver* s, ab200_stats* out) {
 int ab200_synchronize(ab200_solver* s) {
   REQUIRE(s != nullptr, "solver is null");
   CU(cudaSetDevice(s->device));
+  break_chain(s);
   CU(cudaStreamSynchronize(s->stream));
   return AB200_OK;
 }
@@ -1441,6 +1499,7 @@ int ab200_synchronize(ab200_solver* s) {
 int ab200_timer_start(ab200_solver* s) {
   REQUIRE(s != nullptr, "solver is null");
   CU(cudaSetDevice(s->device));
+  break_chain(s);
   if (!s->t0) {
     CU(cudaEventCreate(&s->t0));
     CU(cudaEventCreate(&s->t1));
@@ -1452,6 +1511,7 @@ int ab200_timer_stop(ab200_solver* s, double* elapsed_ms) {
   REQUIRE(s != nullptr && elapsed_ms != nullptr, "null argument");
   if (!s->t0) return set_err(AB200_ESTATE, "ab200_timer_stop without ab200_timer_start");
   CU(cudaSetDevice(s->device));
+  break_chain(s);
   CU(cudaEventRecord(s->t1, s->stream));
   CU(cudaEventSynchronize(s->t1));
   float ms = 0.f;
@@ -1478,6 +1538,10 @@ int ab200_set_option(ab200_solver* s, const char* key, int64_t value) {
     s->opt_halo_fold = (int)value;
   else if (!strcmp(key, "spmv_window"))
     s->opt_spmv_window = (int)value;
+  else if (!strcmp(key, "spmv_win_half"))
+    s->opt_spmv_win_half = (int)value;
+  else if (!strcmp(key, "spmv_ring_warps"))
+    s->opt_spmv_ring_warps = (int)value;
   else if (!strcmp(key, "fused_r"))
     s->opt_fused_r = (int)value;
   else if (!strcmp(key, "fused_stages"))
@@ -1487,6 +1551,7 @@ int ab200_set_option(ab200_solver* s, const char* key, int64_t value) {
   else if (!strcmp(key, "real_mode")) {
     if (value == 0) {
       CU(cudaSetDevice(s->device));
+  break_chain(s);
       int rc = switch_to_complex(s);
       if (rc != AB200_OK) return rc;
     } else if (!s->pristine && !s->real_mode) {

@@ -494,253 +494,349 @@ __global__ void __launch_bounds__(288) spmv_bulk_kernel(SpmvArgs a) {
   }
 }
 
-// ------------------------------------------------------------------ skewed rows: x window in shared memory
-// For operators whose rows are long and uneven (BASELINE config 4: Pareto row lengths, columns in a
-// band around the diagonal plus a sparse far tail) the streaming roofline is not what limits the
-// tile kernel: ncu shows 10 sectors per gather request, L1 hit rate 7% -- every 8/16-byte x
-// entry costs a 32-byte sector through L2.  Here the block first pulls the WINDOW of x its tile
-// can touch around the diagonal into shared memory with one bulk copy (contiguous, so it runs at
-// copy speed and neighbouring tiles hit L2), then streams the tile's values / column ids through
-// a two-stage bulk-copy ring in sub-tiles; all threads first turn a sub-tile into products
-// (coalesced over the entries, x from the window, only out-of-window / ghost entries go to
-// global memory), then rows are summed from the products in stored order (one thread per row,
-// a warp for segments > 64 entries).  Work per block is balanced in non-zeros (the plan's tiles),
-// not in rows.  Rows of <= 16 entries are still summed in scipy's order (bit-identical).
-constexpr int kWinSub = 1024;      // entries per sub-tile
-constexpr int kWinLongSeg = 64;    // segments longer than this are summed by a warp
+// ------------------------------------------------------------------ skewed rows: sliding x ring in shared memory
+// For operators whose rows are long and uneven (BASELINE config 4: Pareto row lengths, columns in
+// a band around the diagonal plus a sparse far tail) the CSR streaming roofline is not what limits
+// the tile kernel: every gathered 8/16-byte x entry costs its own L1 tag look-up and a 32-byte
+// sector through L2 (ncu: 10 sectors per request, L1 hit rate 7%), about one entry per SM clock.
+// This kernel gathers from SHARED memory instead:
+//   * a block owns a CONTIGUOUS range of the plan's nnz tiles (row-aligned, ~equal non-zeros), so
+//     the x entries it can touch around the diagonal slide forward monotonically.  They live in a
+//     power-of-two ring (entry c at slot c & (W-1)); a producer thread extends the ring with bulk
+//     copies (cp.async.bulk + mbarrier) one round AHEAD of the consumers, so every x entry is read
+//     from L2/HBM about once per block and the copy overlaps the arithmetic;
+//   * a round gives every consumer warp one tile.  The warp works alone (no block barrier):
+//     lanes run ALONG THE ENTRIES -- 128-bit loads of 4 column ids and 4 values per lane, all
+//     in flight together -- turn them into products val * x (x from the ring; the few entries
+//     outside it, and ghost entries, are gathered from global memory with the loads issued
+//     together) and park the products in the warp's own strip of shared memory; then lanes run
+//     ALONG THE ROWS and sum each row's products in STORED ORDER (separate multiply and add =
+//     scipy's csr_matvec order: rows of up to 32 entries are bit-identical to scipy); longer
+//     segments are summed by the whole warp (fixed-order butterfly);
+//   * work per warp is balanced in non-zeros, not rows (the merge-path split, snapped to rows);
+//     a row longer than a tile is walked by its warp in strips, carried through y.
+// Rounds are ordered by mbarriers only: ring_full[t % depth] (the producer's copies for round t
+// have landed) and round_done[t % depth] (every consumer warp finished round t).  The warps may
+// drift up to depth - 1 rounds apart -- a tile that holds a 2000-entry row takes its warp four
+// strips while the next three warps find their tiles empty -- and the producer only overwrites
+// ring slots below the window of the oldest round still in flight.
+constexpr int kRingIters = 5;                   // 128-entry groups per strip
+constexpr int kRingStrip = 128 * kRingIters;    // products a warp parks per strip
+constexpr int kRingLongSeg = 32;                // segments longer than this are summed by the warp
+constexpr int kRingRowGroups = 5;               // groups of 32 row pointers fetched ahead per tile
 
-struct WinHdr {
-  int64_t r0, r1;    // rows of the tile
-  int64_t k0, k1;    // its entries
-  int64_t wlo;       // first x entry held in the window
-  int wlen;          // entries held
-  int nrp;           // row pointers staged (from row r0a)
-  int rpoff;
-  int pad;
+constexpr int kRingDepthLog = 3;
+constexpr int kRingDepth = 1 << kRingDepthLog;   // rounds the consumer warps may drift apart
+struct RingHdr {
+  int lo[kRingDepth], hi[kRingDepth];   // x entries [lo, hi) valid in the ring for round t (slot t % depth)
+  int slot[kRingDepth];                 // ring slot of entry lo
 };
 
-template <typename IdxT, typename ValT, typename XT>
-__global__ void __launch_bounds__(288) spmv_window_kernel(SpmvArgs a) {
+struct RingTile {
+  int64_t r0, r1, k0, k1;   // rows and entries of a tile (r0 >= r1: nothing to do)
+};
+
+template <typename IdxT, typename ValT, typename XT, int MAXW>
+__global__ void __launch_bounds__((MAXW + 1) * 32, 1) spmv_ring_kernel(SpmvArgs a) {
   if (a.ctl != nullptr && a.ctl->stop) return;
-  extern __shared__ __align__(128) unsigned char win_smem[];
-  const int nthr = blockDim.x - kWarp;
-  const int ncw = nthr >> 5;
-  const int wcap = a.win_cap;
-  const int rpc = a.rp_cap;
-  // layout: xwin | 2 x (vals | cols) | prod | rptr | long-row list | hdr | barriers
-  size_t off = 0;
-  XT* xwin = reinterpret_cast<XT*>(win_smem);
-  off += ((size_t)wcap * sizeof(XT) + 127) / 128 * 128;
-  unsigned char* ring = win_smem + off;
-  const size_t ring_stage = (size_t)kWinSub * (sizeof(ValT) + sizeof(int32_t));
-  off += 2 * ring_stage;
-  XT* prod = reinterpret_cast<XT*>(win_smem + off);
-  off += (size_t)kWinSub * sizeof(XT);
-  IdxT* srow = reinterpret_cast<IdxT*>(win_smem + off);
-  off += ((size_t)rpc * sizeof(IdxT) + 15) / 16 * 16;
-  int* s_long = reinterpret_cast<int*>(win_smem + off);   // [kWinSub / kWinLongSeg + 2] local row ids
-  off += sizeof(int) * (kWinSub / kWinLongSeg + 4);
-  off = (off + 15) / 16 * 16;
-  WinHdr* hdr = reinterpret_cast<WinHdr*>(win_smem + off);
-  off += sizeof(WinHdr);
-  off = (off + 7) / 8 * 8;
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(win_smem + off);
-  unsigned long long* win_full = bars;        // window + row pointers + header of a tile landed
-  unsigned long long* tile_done = bars + 1;   // every consumer warp is done with the tile
-  unsigned long long* ring_full = bars + 2;   // [2]
-  unsigned long long* ring_empty = bars + 4;  // [2]
-  __shared__ int s_nlong;
+  extern __shared__ __align__(128) unsigned char ring_smem[];
+  const int ncw = (int)(blockDim.x >> 5) - 1;   // consumer warps; the last warp is the producer
+  const int W = a.win_cap;                       // ring capacity in x entries (multiple of 16)
+  XT* ring = reinterpret_cast<XT*>(ring_smem);
+  XT* prod_all = ring + W;
+  unsigned char* tail = reinterpret_cast<unsigned char*>(prod_all + (size_t)ncw * kRingStrip);
+  RingHdr* hdr = reinterpret_cast<RingHdr*>(tail);
+  unsigned long long* ring_full = reinterpret_cast<unsigned long long*>(tail + sizeof(RingHdr));  // [depth]
+  unsigned long long* round_done = ring_full + kRingDepth;                                         // [depth]
+  constexpr int DM = kRingDepth - 1;
+
+  // contiguous share of the tiles for this block
+  const int per = (a.nblocks + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int b0 = (int)blockIdx.x * per;
+  const int b1 = b0 + per < a.nblocks ? b0 + per : a.nblocks;
+  if (b0 >= b1) return;
+  const int rounds = (b1 - b0 + ncw - 1) / ncw;
 
   const int tid = threadIdx.x;
   if (tid == 0) {
-    mbar_init(win_full, 1);
-    mbar_init(tile_done, ncw);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kRingDepth; ++i) {
       mbar_init(ring_full + i, 1);
-      mbar_init(ring_empty + i, ncw);
+      mbar_init(round_done + i, ncw);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
 
-  const IdxT* __restrict__ indptr = static_cast<const IdxT*>(a.indptr);
-  const ValT* __restrict__ values = static_cast<const ValT*>(a.values);
-  const int32_t* __restrict__ indices = a.indices;
-  const XT* __restrict__ x = static_cast<const XT*>(a.x);
   const int64_t* __restrict__ rowblk = a.rowblk;
   const int64_t* __restrict__ nnzblk = a.rowblk + a.nblocks + 1;
-  // contiguous share of the tiles for this block: neighbouring tiles share most of their window
-  const int per = (a.nblocks + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int b0 = (int)blockIdx.x * per;
-  const int b1 = b0 + per < a.nblocks ? b0 + per : a.nblocks;
+  const XT* __restrict__ x = static_cast<const XT*>(a.x);
+  const int nloc = a.n_local_cols > 0x7fffffff ? 0x7fffffff : (int)a.n_local_cols;
+  const int warp = tid >> 5, lane = tid & 31;
 
-  if (tid >= nthr) {
-    // ---------------- producer warp (lane 0)
-    if (tid != nthr) return;
-    constexpr int RA = 16 / (int)sizeof(IdxT);
-    constexpr int XA = 16 / (int)sizeof(XT);  // x entries per 16 bytes
-    unsigned use0 = 0, use1 = 0;  // times each ring stage has been filled
-    const unsigned long long l2pol = l2_policy_evict_first();
-    for (int b = b0, t = 0; b < b1; ++b, ++t) {
-      if (t > 0) mbar_wait(tile_done, (unsigned)(t - 1) & 1u);
-      const int64_t r0 = rowblk[b], r1 = rowblk[b + 1];
-      const int64_t k0 = nnzblk[b], k1 = nnzblk[b + 1];
-      const int64_t nrows = r1 - r0;
-      int64_t half = ((int64_t)wcap - nrows) / 2;
-      if (half < 0) half = 0;
-      int64_t wlo = r0 - half;
-      if (wlo < 0) wlo = 0;
-      wlo &= ~(int64_t)(XA - 1);
-      int64_t whi = wlo + wcap;
-      if (whi > a.n_local_cols) whi = a.n_local_cols;
-      int64_t wlen = whi - wlo;
-      if (wlen < 0) wlen = 0;
-      const int64_t wcopy = (wlen + XA - 1) & ~(int64_t)(XA - 1);  // columns are padded to 16 elements
-      const int64_t r0a = r0 & ~(int64_t)(RA - 1);
-      int64_t nrp = nrows + 1 + (r0 - r0a);
-      if (nrp > rpc) nrp = rpc;
-      nrp = (nrp + RA - 1) & ~(int64_t)(RA - 1);
-      hdr->r0 = r0;
-      hdr->r1 = r1;
-      hdr->k0 = k0;
-      hdr->k1 = k1;
-      hdr->wlo = wlo;
-      hdr->wlen = (int)wlen;
-      hdr->nrp = (int)nrp;
-      hdr->rpoff = (int)(r0 - r0a);
-      const unsigned bw = (unsigned)(wcopy * sizeof(XT)), br = (unsigned)(nrp * sizeof(IdxT));
-      mbar_expect_tx(win_full, bw + br);
-      if (bw) bulk_g2s(xwin, x + wlo, bw, win_full);
-      bulk_g2s(srow, indptr + r0a, br, win_full);
-      // the tile's entries, sub-tile by sub-tile, from the 4-aligned address at or below k0
-      const int64_t ka = k0 & ~(int64_t)3;
-      for (int64_t cs = ka; cs < k1; cs += kWinSub) {
-        const int st = (int)(((cs - ka) / kWinSub) & 1);
-        const unsigned used = st ? use1 : use0;
-        if (used > 0) mbar_wait(ring_empty + st, (used - 1) & 1u);
-        int64_t cnt = k1 - cs;
-        if (cnt > kWinSub) cnt = kWinSub;
-        const unsigned nc = (unsigned)((cnt + 3) & ~(int64_t)3);
-        unsigned char* base = ring + (size_t)st * ring_stage;
-        mbar_expect_tx(ring_full + st, nc * (unsigned)(sizeof(ValT) + 4));
-        bulk_g2s_hint(base, values + cs, nc * (unsigned)sizeof(ValT), ring_full + st, l2pol);
-        bulk_g2s_hint(base + (size_t)kWinSub * sizeof(ValT), indices + cs, nc * 4u, ring_full + st, l2pol);
-        if (st) use1 += 1; else use0 += 1;
+  if (warp == ncw) {
+    // ---------------- producer (lane 0): keeps the ring one round ahead of the consumers
+    if (lane != 0) return;
+    constexpr int XA = 16 / (int)sizeof(XT);                 // x entries per 16 bytes
+    const int nloc_al = (nloc + XA - 1) & ~(XA - 1);          // columns are padded to 16 entries
+    const int H = a.win_half;
+    int cur_lo = 0, whi = 0;   // lower bound of the previous round's window; entries loaded so far
+    int hi_slot = 0, lo_slot = 0;   // ring slots of entries whi and cur_lo
+    for (int t = 0; t < rounds; ++t) {
+      // the consumer warps may be anywhere in rounds (t - depth, t): round t's copies may be
+      // issued once every warp has left round t - depth, and overwrite only slots below the
+      // lower bound of round t - depth + 1
+      if (t >= kRingDepth) mbar_wait(round_done + (t & DM), (unsigned)((t - kRingDepth) >> kRingDepthLog) & 1u);
+      const int bt = b0 + t * ncw;
+      const int bt1 = bt + ncw < b1 ? bt + ncw : b1;
+      const int64_t R0 = rowblk[bt], R1 = rowblk[bt1];
+      int64_t want_lo = R0 - H;
+      if (want_lo < 0) want_lo = 0;
+      if (want_lo > nloc_al) want_lo = nloc_al;
+      want_lo &= ~(int64_t)(XA - 1);
+      int64_t want_hi = R1 + H;
+      if (want_hi > nloc_al) want_hi = nloc_al;
+      want_hi = (want_hi + XA - 1) & ~(int64_t)(XA - 1);
+      int new_hi;
+      if (t == 0) {
+        whi = cur_lo = (int)want_lo;
+        hi_slot = lo_slot = 0;
+        new_hi = (int)(want_hi < want_lo + W ? want_hi : want_lo + W);
+      } else {
+        const int oldest = t - kRingDepth + 1 > 0 ? t - kRingDepth + 1 : 0;
+        const int64_t cap = (int64_t)hdr->lo[oldest & DM] + W;   // that round still reads from its lo on
+        const int64_t h = want_hi < cap ? want_hi : cap;
+        new_hi = h > whi ? (int)h : whi;
       }
+      int next_lo = (int)want_lo;
+      if (next_lo < new_hi - W) next_lo = new_hi - W;
+      if (next_lo > new_hi) next_lo = new_hi;
+      if (next_lo < cur_lo) next_lo = cur_lo;
+      lo_slot += next_lo - cur_lo;   // < 2 W: one conditional subtraction
+      if (lo_slot >= W) lo_slot -= W;
+      hdr->lo[t & DM] = next_lo;
+      hdr->hi[t & DM] = new_hi;
+      hdr->slot[t & DM] = lo_slot;
+      const int cnt = new_hi - whi;   // multiple of XA, <= W
+      mbar_expect_tx(ring_full + (t & DM), (unsigned)cnt * (unsigned)sizeof(XT));  // release: hdr visible
+      if (cnt > 0) {
+        const int first = cnt < W - hi_slot ? cnt : W - hi_slot;
+        bulk_g2s(ring + hi_slot, x + whi, (unsigned)first * (unsigned)sizeof(XT), ring_full + (t & DM));
+        if (cnt > first)
+          bulk_g2s(ring, x + whi + first, (unsigned)(cnt - first) * (unsigned)sizeof(XT), ring_full + (t & DM));
+        hi_slot += cnt;
+        if (hi_slot >= W) hi_slot -= W;
+      }
+      whi = new_hi;
+      cur_lo = next_lo;
     }
     return;
   }
 
-  // ---------------- consumers
+  // ---------------- consumer warps
+  const IdxT* __restrict__ indptr = static_cast<const IdxT*>(a.indptr);
+  const ValT* __restrict__ values = static_cast<const ValT*>(a.values);
+  const int32_t* __restrict__ indices = a.indices;
   const XT* __restrict__ ghost = static_cast<const XT*>(a.ghost);
   XT* __restrict__ yout = static_cast<XT*>(a.y);
-  const int64_t nloc = a.n_local_cols;
+  XT* prod = prod_all + (size_t)warp * kRingStrip;
   const double xs = a.xscale ? *a.xscale : 1.0;
-  const int lane = tid & 31, warp = tid >> 5;
-  unsigned use0 = 0, use1 = 0;
-  for (int b = b0, t = 0; b < b1; ++b, ++t) {
-    mbar_wait(win_full, (unsigned)t & 1u);
-    const WinHdr h = *hdr;
-    const int64_t ka = h.k0 & ~(int64_t)3;
-    const int nrows = (int)(h.r1 - h.r0);
-    if (h.k1 == h.k0) {  // only empty rows
-      for (int rl = tid; rl < nrows; rl += nthr) yout[h.r0 + rl] = xzero<XT>();
+  const unsigned long long l2pol = l2_policy_evict_first();  // CSR streams must not evict x from L2
+  constexpr int VQ = (int)sizeof(ValT) / 4;   // 16-byte loads that hold 4 values
+
+  auto load_tile = [&](int tt) {
+    RingTile T = {0, 0, 0, 0};
+    const int b = b0 + tt * ncw + warp;
+    if (tt < rounds && b < b1) {
+      T.r0 = rowblk[b], T.r1 = rowblk[b + 1];
+      T.k0 = nnzblk[b], T.k1 = nnzblk[b + 1];
     }
-    for (int64_t cs = ka; cs < h.k1; cs += kWinSub) {
-      const int st = (int)(((cs - ka) / kWinSub) & 1);
-      mbar_wait(ring_full + st, (st ? use1 : use0) & 1u);
-      if (st) use1 += 1; else use0 += 1;
-      const ValT* sval = reinterpret_cast<const ValT*>(ring + (size_t)st * ring_stage);
-      const int32_t* scol =
-          reinterpret_cast<const int32_t*>(ring + (size_t)st * ring_stage + (size_t)kWinSub * sizeof(ValT));
-      int64_t ce = cs + kWinSub;
-      if (ce > h.k1) ce = h.k1;
-      const int cnt = (int)(ce - cs);
-      // ---- products, coalesced over the entries; the (few) gathers that miss the window are
-      //      issued together so a thread waits for global memory once per sub-tile, not per entry
-      constexpr int PU = 4;
-      for (int k0 = tid; k0 < cnt; k0 += PU * nthr) {
-        XT xg[PU];
-        int64_t wi[PU];
+    return T;
+  };
+
+  // registers of the strip in flight: 4 column ids + 4 values per lane and 128-entry group, and
+  // (first strip of a tile) the tile's first kRingRowGroups x 32 row pointers, one per lane
+  int4 cc[kRingIters];
+  double2 vv[kRingIters][VQ];
+  IdxT rp[kRingRowGroups], nrp[kRingRowGroups];
+  auto issue_loads = [&](int64_t ca, int64_t k1) {
+    const int tot = (int)((ca + kRingStrip < k1 ? ca + kRingStrip : k1) - ca);
 #pragma unroll
-        for (int u = 0; u < PU; ++u) {
-          const int k = k0 + u * nthr;
-          wi[u] = -1;
-          xg[u] = xzero<XT>();
-          if (k < cnt) {
-            const int64_t col = scol[k];
-            wi[u] = col - h.wlo;
-            if (wi[u] < 0 || wi[u] >= h.wlen) {
-              xg[u] = (col < nloc) ? ld_ro(x + col) : ld_ro(ghost + (col - nloc));
-              wi[u] = -1;
-            }
+    for (int it = 0; it < kRingIters; ++it) {
+      const int g = it * kWarp + lane;
+      if (4 * g < tot) {
+        cc[it] = ld_stream_ef(reinterpret_cast<const int4*>(indices + ca) + g, l2pol);
+#pragma unroll
+        for (int q = 0; q < VQ; ++q)
+          vv[it][q] = ld_stream_ef(reinterpret_cast<const double2*>(values + ca) + (size_t)g * VQ + q, l2pol);
+      }
+    }
+  };
+  auto issue_rowptr = [&](const RingTile& T) {
+#pragma unroll
+    for (int q = 0; q < kRingRowGroups; ++q) {
+      int64_t row = T.r0 + q * kWarp + lane;
+      if (row > T.r1) row = T.r1;
+      nrp[q] = indptr[row];
+    }
+  };
+  int t = 0;
+  RingTile cur = load_tile(0), nxt = load_tile(1);
+  // rounds in which this warp has no rows still take part in the hand-shake, in order
+  auto skip_idle = [&]() {
+    while (t < rounds && cur.r0 >= cur.r1) {
+      mbar_wait(ring_full + (t & DM), (unsigned)(t >> kRingDepthLog) & 1u);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(round_done + (t & DM));
+      ++t;
+      cur = nxt;
+      nxt = load_tile(t + 1);
+    }
+  };
+  skip_idle();
+  int64_t ca = cur.k0 & ~(int64_t)3, cs = cur.k0;
+  if (t < rounds) {
+    issue_loads(ca, cur.k1);
+    issue_rowptr(cur);
+  }
+  int wlo = 0, wslot = 0;
+  unsigned wlen = 0;
+  while (t < rounds) {
+    // strips of kRingStrip entries starting at the 4-entry-aligned address at or below k0 (the few
+    // leading entries belong to the previous tile: computed, never read back)
+    const int64_t ce = ca + kRingStrip < cur.k1 ? ca + kRingStrip : cur.k1;
+    const int tot = (int)(ce - ca);
+    const bool first = (cs == cur.k0);
+    if (first) {
+      mbar_wait(ring_full + (t & DM), (unsigned)(t >> kRingDepthLog) & 1u);
+      wlo = hdr->lo[t & DM];
+      wslot = hdr->slot[t & DM];
+      int whi = hdr->hi[t & DM];
+      if (whi > nloc) whi = nloc;   // the padding entry after an odd-length column is not x
+      wlen = whi > wlo ? (unsigned)(whi - wlo) : 0u;
+#pragma unroll
+      for (int q = 0; q < kRingRowGroups; ++q) rp[q] = nrp[q];
+    }
+    // ---- products, lanes along the entries.  Entries outside the ring (the far tail, ghost
+    //      columns) are gathered from global memory; so that nothing branches and the four
+    //      gathers of a group are in flight together, EVERY entry issues one: in-ring entries
+    //      read the same dummy address (one broadcast sector per request, an L1 hit).  Measured
+    //      against two alternatives on the power-law operator (n = 1e7, profiles/r02_spmv_ring.md):
+    //      listing the out-of-ring entries in shared memory and gathering them one per lane
+    //      (+17%), and one predicated gather per group of four issued ahead for all groups (+11%)
+#pragma unroll
+    for (int it = 0; it < kRingIters; ++it) {
+      const int g = it * kWarp + lane;
+      if (4 * g < tot) {
+        const int col[4] = {cc[it].x, cc[it].y, cc[it].z, cc[it].w};
+        XT xg[4];
+        unsigned off[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          off[u] = (unsigned)(col[u] - wlo);
+          const XT* src = (col[u] < nloc) ? x + col[u] : ghost + (col[u] - nloc);
+          xg[u] = ld_ro(off[u] < wlen ? x : src);
+        }
+        XT pr[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          XT xv = xg[u];
+          if (off[u] < wlen) {
+            int sl = (int)off[u] + wslot;
+            if (sl >= W) sl -= W;
+            xv = ring[sl];
+          }
+          if constexpr (sizeof(ValT) == 8) {
+            const double2 two = vv[it][u >> 1];
+            pr[u] = vmul((u & 1) ? two.y : two.x, xv);
+          } else {
+            pr[u] = vmul(vv[it][u], xv);
           }
         }
+        if constexpr (sizeof(XT) == 8) {
+          double2* dst = reinterpret_cast<double2*>(prod + 4 * g);
+          dst[0] = make_double2(pr[0], pr[1]);
+          dst[1] = make_double2(pr[2], pr[3]);
+        } else {
 #pragma unroll
-        for (int u = 0; u < PU; ++u) {
-          const int k = k0 + u * nthr;
-          if (k < cnt) prod[k] = vmul(sval[k], wi[u] >= 0 ? xwin[wi[u]] : xg[u]);
+          for (int u = 0; u < 4; ++u) prod[4 * g + u] = pr[u];
         }
       }
-      if (tid == 0) s_nlong = 0;
-      __syncwarp();
-      if (lane == 0) mbar_arrive(ring_empty + st);   // values / column ids of this stage are consumed
-      asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");   // products visible to all consumers
-      // ---- rows: one thread per row over the products, stored order
-      const int64_t lo_k = cs > h.k0 ? cs : h.k0;
-      for (int rl = tid; rl < nrows; rl += nthr) {
-        const int slot = h.rpoff + rl;
-        int64_t rs, re;
-        if (slot + 1 < h.nrp) {
-          rs = (int64_t)srow[slot];
-          re = (int64_t)srow[slot + 1];
-        } else {
-          rs = (int64_t)indptr[h.r0 + rl];
-          re = (int64_t)indptr[h.r0 + rl + 1];
-        }
-        if (re <= lo_k && !(rs == re && cs == ka)) continue;  // finished in an earlier sub-tile
-        if (rs >= ce && rs != re) continue;                    // starts in a later one
-        const int64_t lo = rs > lo_k ? rs : lo_k;
-        const int64_t hi = re < ce ? re : ce;
-        if (hi - lo > kWinLongSeg) {
-          const int q = atomicAdd(&s_nlong, 1);
-          s_long[q] = rl;
-          continue;
-        }
-        XT acc = (rs < lo_k) ? yout[h.r0 + rl] : xzero<XT>();
-        for (int k = (int)(lo - cs); k < (int)(hi - cs); ++k) acc = cadd_rn(acc, prod[k]);
-        if (re <= ce) acc = cscale(acc, xs);
-        yout[h.r0 + rl] = acc;
-      }
-      asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");   // the long-row list is complete
-      const int nlong = s_nlong;
-      for (int l = warp; l < nlong; l += ncw) {
-        const int rl = s_long[l];
-        const int slot = h.rpoff + rl;
-        int64_t rs, re;
-        if (slot + 1 < h.nrp) {
-          rs = (int64_t)srow[slot];
-          re = (int64_t)srow[slot + 1];
-        } else {
-          rs = (int64_t)indptr[h.r0 + rl];
-          re = (int64_t)indptr[h.r0 + rl + 1];
-        }
-        const int64_t lo = rs > lo_k ? rs : lo_k;
-        const int64_t hi = re < ce ? re : ce;
-        XT acc = xzero<XT>();
-        for (int k = (int)(lo - cs) + lane; k < (int)(hi - cs); k += kWarp) acc = cadd_rn(acc, prod[k]);
-        acc = warp_sum(acc);
-        if (lane == 0) {
-          XT tsum = (rs < lo_k) ? cadd_rn(yout[h.r0 + rl], acc) : acc;
-          if (re <= ce) tsum = cscale(tsum, xs);
-          yout[h.r0 + rl] = tsum;
-        }
-      }
-      asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");   // products / list may be overwritten
+    }
+    // ---- the next strip's entries go in flight before this strip's rows are summed
+    const bool more = ca + kRingStrip < cur.k1;
+    bool prefetched = false;
+    if (more) {
+      issue_loads(ca + kRingStrip, cur.k1);
+      prefetched = true;
+    } else if (t + 1 < rounds && nxt.r0 < nxt.r1) {
+      issue_loads(nxt.k0 & ~(int64_t)3, nxt.k1);
+      issue_rowptr(nxt);
+      prefetched = true;
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(tile_done);
+    // ---- rows, lanes along the rows, stored order
+    int grp = 0;
+    for (int64_t rb = cur.r0; rb < cur.r1; rb += kWarp, ++grp) {
+      const int64_t row = rb + lane;
+      const bool act = row < cur.r1;
+      int64_t rs, re;
+      if (grp < kRingRowGroups - 1) {
+        // row pointers fetched ahead: lane l holds indptr[rb + l]; its row ends where the next begins
+        IdxT mine = rp[0], next0 = rp[1];
+#pragma unroll
+        for (int q = 1; q < kRingRowGroups - 1; ++q)
+          if (grp == q) mine = rp[q], next0 = rp[q + 1];
+        IdxT up = __shfl_down_sync(0xffffffffu, mine, 1);
+        const IdxT wrap = __shfl_sync(0xffffffffu, next0, 0);
+        if (lane == kWarp - 1) up = wrap;
+        rs = act ? (int64_t)mine : 0;
+        re = act ? (int64_t)up : 0;
+      } else {
+        rs = act ? (int64_t)indptr[row] : 0;
+        re = act ? (int64_t)indptr[row + 1] : 0;
+      }
+      const int64_t lo = rs > cs ? rs : cs;
+      const int64_t hi = re < ce ? re : ce;
+      const bool has = act && (hi > lo || (rs == re && first));
+      const int kb = (int)(lo - ca), ke = (int)(hi - ca);
+      const bool lng = has && (ke - kb > kRingLongSeg);
+      XT acc = xzero<XT>();
+      if (has && rs < cs) acc = yout[row];
+      if (has && !lng)
+        for (int k = kb; k < ke; ++k) acc = cadd_rn(acc, prod[k]);
+      unsigned m = __ballot_sync(0xffffffffu, lng);
+      while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        const int sb = __shfl_sync(0xffffffffu, kb, src);
+        const int se = __shfl_sync(0xffffffffu, ke, src);
+        XT part = xzero<XT>();
+        for (int k = sb + lane; k < se; k += kWarp) part = cadd_rn(part, prod[k]);
+        part = warp_sum(part);
+        if (lane == src) acc = cadd_rn(acc, part);
+      }
+      if (has) yout[row] = (re <= ce) ? cscale(acc, xs) : acc;
+    }
+    __syncwarp();   // the strip of products may be overwritten
+    if (more) {
+      ca += kRingStrip;
+      cs = ca;
+    } else {
+      if (lane == 0) mbar_arrive(round_done + (t & DM));
+      ++t;
+      cur = nxt;
+      nxt = load_tile(t + 1);
+      if (!prefetched) {
+        skip_idle();
+        if (t < rounds) {
+          issue_loads(cur.k0 & ~(int64_t)3, cur.k1);
+          issue_rowptr(cur);
+        }
+      }
+      ca = cur.k0 & ~(int64_t)3;
+      cs = cur.k0;
+    }
   }
 }
 
@@ -815,7 +911,7 @@ static cudaError_t launch_spmv_ttl(const SpmvArgs& a, cudaStream_t st) {
   static PerDeviceOnce once;
   if (once.first_use()) {
     cudaFuncSetAttribute(spmv_tile_kernel<IdxT, ValT, XT, THREADS, LONG>,
-                         cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   }
   int grid = a.nblocks;  // one tile per block; blocks are small and many per SM
   if (a.contig) {
@@ -890,42 +986,49 @@ static cudaError_t launch_spmv_bulk(const SpmvArgs& a, cudaStream_t st) {
               : launch_spmv_bulk_h<IdxT, ValT, XT, false>(a, st);
 }
 
-size_t spmv_window_smem(int win_cap, int rp_cap, int val_bytes, int idx_bytes, int x_bytes) {
-  size_t off = ((size_t)win_cap * x_bytes + 127) / 128 * 128;
-  off += 2 * (size_t)kWinSub * (val_bytes + 4);
-  off += (size_t)kWinSub * x_bytes;
-  off += ((size_t)rp_cap * idx_bytes + 15) / 16 * 16;
-  off += sizeof(int) * (kWinSub / kWinLongSeg + 4);
-  off = (off + 15) / 16 * 16;
-  off += sizeof(WinHdr);
-  off = (off + 7) / 8 * 8;
-  return off + 6 * sizeof(unsigned long long);
+size_t spmv_ring_smem(int win_cap, int nwarps, int x_bytes) {
+  return (size_t)win_cap * x_bytes + (size_t)nwarps * kRingStrip * x_bytes + sizeof(RingHdr) +
+         2 * kRingDepth * sizeof(unsigned long long);
 }
 
 template <typename IdxT, typename ValT, typename XT>
-static cudaError_t launch_spmv_window(const SpmvArgs& a, cudaStream_t st) {
-  const size_t smem = spmv_window_smem(a.win_cap, a.rp_cap, sizeof(ValT), sizeof(IdxT), sizeof(XT));
-  const int threads = 256 + kWarp;
+static cudaError_t launch_spmv_ring(const SpmvArgs& a, cudaStream_t st) {
+  constexpr int MAXW = sizeof(XT) == 8 ? 15 : 7;   // + the producer warp = 16 / 8 warps; 16-byte products: half the warps fit
+  int nwarps = a.ring_warps;
+  if (nwarps > MAXW) nwarps = MAXW;
+  if (nwarps < 1) nwarps = 1;
+  // the ring takes what the strips of products leave of the 227 KB, up to the capacity asked for
+  int wcap = a.win_cap;
+  const int fit = (int)((227 * 1024 - spmv_ring_smem(0, nwarps, sizeof(XT))) / sizeof(XT)) / 256 * 256;
+  if (wcap > fit) wcap = fit;
+  wcap = wcap / 16 * 16;
+  if (wcap < 256) wcap = 256;
+  SpmvArgs b = a;
+  b.win_cap = wcap;
+  if (b.win_half > (wcap - 1536) / 2) b.win_half = (wcap - 1536) / 2;   // room for two rounds of rows
+  if (b.win_half < 0) b.win_half = 0;
+  const size_t smem = spmv_ring_smem(wcap, nwarps, sizeof(XT));
   static PerDeviceOnce once;
   if (once.first_use()) {
-    cudaFuncSetAttribute(spmv_window_kernel<IdxT, ValT, XT>,
-                         cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    cudaFuncSetAttribute(spmv_ring_kernel<IdxT, ValT, XT, MAXW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         227 * 1024);
   }
-  int occ = 1;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmv_window_kernel<IdxT, ValT, XT>, threads,
-                                                    smem) != cudaSuccess || occ < 1)
-    occ = 1;
-  if (a.bps > 0 && a.bps < occ) occ = a.bps;
-  int64_t grid = (int64_t)a.num_sms * occ;
-  if (grid > a.nblocks) grid = a.nblocks;
+  int64_t grid = a.num_sms;   // one block per SM: the ring wants the shared memory
+  if (a.bps > 1) grid *= a.bps;   // (A/B only: more, smaller ranges per SM-resident block)
+  const int64_t need = (a.nblocks + nwarps - 1) / nwarps;   // no block without a full round of tiles
+  if (grid > need) grid = need;
   if (grid < 1) grid = 1;
-  spmv_window_kernel<IdxT, ValT, XT><<<(int)grid, threads, smem, st>>>(a);
+  spmv_ring_kernel<IdxT, ValT, XT, MAXW><<<(int)grid, (nwarps + 1) * kWarp, smem, st>>>(b);
   return cudaGetLastError();
 }
 
 template <typename IdxT, typename ValT, typename XT, int THREADS>
 static cudaError_t launch_spmv_tt(const SpmvArgs& a, cudaStream_t st) {
-  if (a.window) return launch_spmv_window<IdxT, ValT, XT>(a, st);
+  // the ring kernel serves float64 vectors (real storage); with complex128 vectors half as many
+  // entries fit the ring and the strips, and the tile kernel is faster (1.33 vs 2.0 ms, n = 1e7)
+  if constexpr (sizeof(XT) == 8) {
+    if (a.window) return launch_spmv_ring<IdxT, ValT, XT>(a, st);
+  }
   if (!a.long_rows && a.variant == 0) return launch_spmv_bulk<IdxT, ValT, XT>(a, st);
   if (!a.long_rows && a.variant == 2) return launch_spmv_stream<IdxT, ValT, XT, THREADS>(a, st);
   return a.long_rows ? launch_spmv_ttl<IdxT, ValT, XT, THREADS, true>(a, st)

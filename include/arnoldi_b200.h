@@ -47,14 +47,19 @@ extern "C" {
 #define AB200_ORTHO_MGS 1  /* dgks_mgs, ortho.py:9-53 */
 
 /* spmv_algo for ab200_set_csr */
-#define AB200_SPMV_AUTO 0   /* STREAM when no row has more than 16 entries, else MERGE         */
-#define AB200_SPMV_VECTOR 1 /* row-snapped nnz tiles; a warp sums every segment > 16 entries   */
+#define AB200_SPMV_AUTO 0   /* STREAM when no row has more than 16 entries; else MERGE when at   \
+                               least half of the (sampled) entries lie within the ring's reach   \
+                               of the diagonal, else VECTOR                                      */
+#define AB200_SPMV_VECTOR 1 /* nnz tiles snapped to rows, one block per tile, x gathered from    \
+                               global memory; a warp sums every segment > 16 entries            */
 #define AB200_SPMV_STREAM 2 /* one thread per row, tiles moved by bulk copies (TMA) through a   \
                                shared-memory ring; rows of <= 16 entries only (else EINVAL);    \
                                bit-identical to scipy's csr_matvec                              */
-#define AB200_SPMV_MERGE 3  /* equal-nnz tiles cut INSIDE rows (merge-path), partial row sums   \
-                               fixed up in tile order; x window of banded operators staged in   \
-                               shared memory                                                    */
+#define AB200_SPMV_MERGE 3  /* skewed rows: equal-nnz tiles snapped to rows (the merge-path      \
+                               split), one WARP per tile, lanes along the entries for the        \
+                               products and along the rows for the sums; x gathered from a      \
+                               shared-memory ring that slides along the diagonal (bulk copies).  \
+                               float64 vectors (real storage); complex128 vectors use VECTOR    */
 
 typedef struct ab200_solver ab200_solver; /* opaque */
 
@@ -230,6 +235,9 @@ int ab200_timer_stop(ab200_solver *s, double *elapsed_ms);
  *   "spmv_threads"    SpMV block size, 128 or 256        } take effect at the next
  *   "spmv_stages"     ring depth of the bulk pipeline    } ab200_set_csr
  *   "spmv_bps"        resident SpMV blocks per SM (0 = what fits)
+ *   "spmv_window"     MERGE: ring capacity in x entries (multiple of 256, <= 16384)  } at the next
+ *   "spmv_win_half"   MERGE: entries kept on each side of a round's rows             } ab200_set_csr
+ *   "spmv_ring_warps" MERGE: consumer warps per block (<= 15)
  *   "halo_fold"       0 = separate halo gather kernel before each SpMV (default 1: banded
  *                     operators read their halo inside the SpMV) */
 int ab200_set_option(ab200_solver *s, const char *key, int64_t value);

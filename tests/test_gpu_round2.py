@@ -449,12 +449,14 @@ def _local_skewed(n, rng, long_rows=()):
 
 
 @pytest.mark.parametrize("opts", [dict(), dict(spmv_tile=1024), dict(spmv_window=2048),
-                                  dict(spmv_tile=8192, spmv_bps=1)])
+                                  dict(spmv_tile=8192, spmv_bps=2),
+                                  dict(spmv_window=1024, spmv_ring_warps=3, spmv_tile=256),
+                                  dict(spmv_win_half=100), dict(spmv_tile=640, spmv_ring_warps=1)])
 def test_spmv_window_kernel(gpu, opts):
-    """Skewed rows with local columns (AB200_SPMV_MERGE / AUTO): x window in shared memory.
-    Rows of <= 16 entries stay bit-identical to scipy; longer ones within 1e-13 of the row's
-    absolute sum.  Real and complex vectors, complex values, rows longer than several tiles,
-    runs of empty rows."""
+    """Skewed rows with local columns (AB200_SPMV_MERGE / AUTO): x gathered from a sliding ring
+    in shared memory (spmv_ring_kernel), every ring / tile / warp shape.  Rows of <= 16 entries
+    stay bit-identical to scipy; longer ones within 1e-13 of the row's absolute sum.  Real and
+    complex vectors, complex values, rows longer than several tiles, runs of empty rows."""
     from arnoldi_b200.matrices import powerlaw
     from arnoldi_b200.solver import DeviceSolver
     rng = np.random.default_rng(12)
