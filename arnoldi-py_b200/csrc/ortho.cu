@@ -32,6 +32,42 @@ __device__ __forceinline__ double sum_partials(const double* part, int nblocks, 
   return warp_sum(a);
 }
 
+// Last block: red[2i], red[2i+1] = sum over blocks of column i's partial, red[2c] = sum of the
+// norm partials.  Same arithmetic per column as sum_partials (lanes stride the blocks, fixed
+// butterfly), but a warp takes FOUR columns at a time so that their loads are all in flight
+// together: the last block is alone on the device here and every dependent L2 round trip of
+// its tail is paid by the whole grid (and, on several GPUs, by every rank waiting for it).
+__device__ __forceinline__ void reduce_partials(const cplx* part, int gcap, const double* npart, int nblocks,
+                                                int c, double* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  constexpr int G = 4;
+  for (int i0 = warp * G; i0 < c; i0 += nwarps * G) {
+    cplx acc[G];
+#pragma unroll
+    for (int k = 0; k < G; ++k) acc[k] = make_double2(0.0, 0.0);
+    for (int b = lane; b < nblocks; b += kWarp) {
+      cplx v[G];
+#pragma unroll
+      for (int k = 0; k < G; ++k)
+        v[k] = (i0 + k < c) ? part[(size_t)(i0 + k) * gcap + b] : make_double2(0.0, 0.0);
+#pragma unroll
+      for (int k = 0; k < G; ++k) acc[k] = cadd(acc[k], v[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < G; ++k) {
+      const cplx g = warp_sum(acc[k]);
+      if (lane == 0 && i0 + k < c) {
+        red[2 * (i0 + k)] = g.x;
+        red[2 * (i0 + k) + 1] = g.y;
+      }
+    }
+  }
+  if (warp == nwarps - 1) {   // the warp with the fewest columns
+    const double s = sum_partials(npart, nblocks, lane);
+    if (lane == 0) red[2 * c] = s;
+  }
+}
+
 // Cross-GPU sum of `count` doubles held in red[] (local result), in rank order.
 // Called by every thread of the last block; returns with red[] = global sums.
 //
@@ -260,17 +296,7 @@ __global__ void __launch_bounds__(CT < 8 ? 256 : 512) cgs_pass1_kernel(OrthoArgs
   // ---- last block: reduce across blocks (fixed order), across GPUs, finish
   extern __shared__ double red[];  // 2*c + 1 doubles
   const int nwarps = blockDim.x >> 5;
-  for (int i = warp; i < c; i += nwarps) {
-    cplx g = sum_partials(a.part + (size_t)i * gcap, gridDim.x, lane);
-    if (lane == 0) {
-      red[2 * i] = g.x;
-      red[2 * i + 1] = g.y;
-    }
-  }
-  if (warp == 0) {
-    double s = sum_partials(a.npart, gridDim.x, lane);
-    if (lane == 0) red[2 * c] = s;
-  }
+  reduce_partials(a.part, gcap, a.npart, gridDim.x, c, red);
   __syncthreads();
   peer_allreduce(a.comm, red, 2 * c + 1, ctl);
   __syncthreads();
@@ -588,17 +614,7 @@ __global__ void __launch_bounds__(CT < 5 ? 256 : 512) cgs_fused_kernel(OrthoArgs
   if (!last_block_ticket(a.ticket, gridDim.x, &s_last)) return;
 
   double* red = reinterpret_cast<double*>(fused_smem);  // 2*c + 1 doubles (spart is free now)
-  for (int i = warp; i < c; i += nwarps) {
-    cplx g = sum_partials(a.part + (size_t)i * gcap, gridDim.x, lane);
-    if (lane == 0) {
-      red[2 * i] = g.x;
-      red[2 * i + 1] = g.y;
-    }
-  }
-  if (warp == 0) {
-    double s = sum_partials(a.npart, gridDim.x, lane);
-    if (lane == 0) red[2 * c] = s;
-  }
+  reduce_partials(a.part, gcap, a.npart, gridDim.x, c, red);
   __syncthreads();
   peer_allreduce(a.comm, red, 2 * c + 1, ctl);
   __syncthreads();
@@ -811,17 +827,7 @@ __global__ void __launch_bounds__(MAXT) cgs_fused_pipe_kernel(OrthoArgs a) {
   if (!last_block_ticket(a.ticket, gridDim.x, &s_last)) return;
 
   double* red = reinterpret_cast<double*>(fused_smem);  // 2*c + 1 doubles (spart is free now)
-  for (int i = warp; i < c; i += nwarps) {
-    cplx g = sum_partials(a.part + (size_t)i * gcap, gridDim.x, lane);
-    if (lane == 0) {
-      red[2 * i] = g.x;
-      red[2 * i + 1] = g.y;
-    }
-  }
-  if (warp == 0) {
-    double s = sum_partials(a.npart, gridDim.x, lane);
-    if (lane == 0) red[2 * c] = s;
-  }
+  reduce_partials(a.part, gcap, a.npart, gridDim.x, c, red);
   __syncthreads();
   peer_allreduce(a.comm, red, 2 * c + 1, ctl);
   __syncthreads();
@@ -958,17 +964,7 @@ __global__ void __launch_bounds__(256) cgs_fused_warp_kernel(OrthoArgs a) {
   if (!last_block_ticket(a.ticket, gridDim.x, &s_last)) return;
 
   double* red = reinterpret_cast<double*>(fw_smem);  // 2*c + 1 doubles
-  for (int k = warp; k < c; k += nwarps) {
-    cplx g = sum_partials(a.part + (size_t)k * gcap, gridDim.x, lane);
-    if (lane == 0) {
-      red[2 * k] = g.x;
-      red[2 * k + 1] = g.y;
-    }
-  }
-  if (warp == 0) {
-    double sN = sum_partials(a.npart, gridDim.x, lane);
-    if (lane == 0) red[2 * c] = sN;
-  }
+  reduce_partials(a.part, gcap, a.npart, gridDim.x, c, red);
   __syncthreads();
   peer_allreduce(a.comm, red, 2 * c + 1, ctl);
   __syncthreads();

@@ -223,7 +223,9 @@ static void resolve_pending(ab200_solver* s, const int* step_round2 /* may be nu
     if (t.step >= 0 && s->h_ctl && s->h_ctl->stop && t.step > s->h_ctl->broke_at) executed = false;
     t.executed = executed ? 1 : 0;
   }
-  if (!flush && s->pending.size() < 4096) return;
+  // (bounded backlog: every pending launch holds a CUDA event, and events are slow to create and
+  //  destroy -- 4096 of them cost 0.9 s at teardown)
+  if (!flush && s->pending.size() < 512) return;
   for (auto& t : s->pending) {
     const bool executed = t.executed != 0;
     float ms = 0.f;
