@@ -13,6 +13,7 @@
 
 #include <string>
 #include <thread>
+#include <chrono>
 #include <vector>
 
 #include "../../include/arnoldi_b200.h"
@@ -158,6 +159,7 @@ struct ab200_solver {
   bool real_mode = true;
   bool pristine = true;   // no column has been written yet
   cudaEvent_t chain_event = nullptr;   // end event of the launch enqueued last, while nothing followed it
+  bool pooled = false;   // big buffers come from the device's stream-ordered pool (single-GPU blocks)
 };
 
 static cudaEvent_t get_event(ab200_solver* s) {
@@ -209,6 +211,27 @@ struct LaunchScope {
 };
 // anything enqueued outside a LaunchScope ends the chain of shared boundary events
 static inline void break_chain(ab200_solver* s) { s->chain_event = nullptr; }
+
+// The multi-GB buffers (basis, CSR arrays) of a solver that owns the WHOLE operator come from the
+// device's stream-ordered memory pool, with the pool told to keep what is freed: cudaFree of an
+// 11 GB basis was measured at 0.08-1.2 s (it hands the pages back to the OS), a large share of a
+// short solve; the next solver of the process gets the memory back in microseconds.  A block of a
+// sharded operator keeps cudaMalloc: its basis is exported over CUDA IPC, which pool memory is not.
+static cudaError_t big_alloc(ab200_solver* s, void** p, size_t bytes) {
+  if (!s->pooled) return cudaMalloc(p, bytes);
+  return cudaMallocAsync(p, bytes, s->stream);
+}
+template <typename T>
+static cudaError_t big_alloc(ab200_solver* s, T** p, size_t bytes) {
+  return big_alloc(s, reinterpret_cast<void**>(p), bytes);
+}
+static void big_free(ab200_solver* s, void* p) {
+  if (p == nullptr) return;
+  if (s->pooled && s->stream)
+    cudaFreeAsync(p, s->stream);
+  else
+    cudaFree(p);
+}
 
 // Mark which pending launches really ran (needs the expansion's flags: cheap, no CUDA call) and,
 // when `flush` or the backlog is large, read their event times and fold them into the stats.
@@ -429,10 +452,22 @@ int ab200_comm_disconnect(ab200_solver* s) {
 
 int ab200_destroy(ab200_solver* s) {
   if (!s) return AB200_OK;
+  const bool trace = getenv("AB200_TRACE_DESTROY") != nullptr;
+  auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double tm = now();
+  auto lap = [&](const char* what) {
+    if (!trace) return;
+    const double t = now();
+    fprintf(stderr, "[ab200_destroy] %-12s %.4f s\n", what, t - tm);
+    tm = t;
+  };
   cudaSetDevice(s->device);
   if (s->stream) cudaStreamSynchronize(s->stream);
+  lap("sync");
   resolve_pending(s, nullptr, true);
+  lap("flush");
   for (auto e : s->pool) cudaEventDestroy(e);
+  lap("events");
   if (s->t0) cudaEventDestroy(s->t0), cudaEventDestroy(s->t1);
   // imports first (a no-op after ab200_comm_disconnect), then the buffers this rank owns
   for (int r = 0; r < kMaxRanks; ++r) {
@@ -442,19 +477,25 @@ int ab200_destroy(ab200_solver* s) {
     if (s->peer_ghost[r]) cudaIpcCloseMemHandle(s->peer_ghost[r]);
     if (s->peer_hflags[r]) cudaIpcCloseMemHandle(s->peer_hflags[r]);
   }
-  cudaFree(s->V), cudaFree(s->wtmp), cudaFree(s->xtmp), cudaFree(s->scale), cudaFree(s->Hdev);
+  lap("ipc close");
+  big_free(s, s->V), big_free(s, s->wtmp), big_free(s, s->xtmp), cudaFree(s->scale), cudaFree(s->Hdev);
+  lap("free V");
   cudaFree(s->hscratch), cudaFree(s->coef), cudaFree(s->part), cudaFree(s->npart);
   cudaFree(s->ticket), cudaFree(s->ctl), cudaFree(s->step_round2), cudaFree(s->qdev);
-  cudaFree(s->indptr), cudaFree(s->indices), cudaFree(s->values), cudaFree(s->rowblk);
+  big_free(s, s->indptr), big_free(s, s->indices), big_free(s, s->values), cudaFree(s->rowblk);
+  if (s->pooled && s->stream) cudaStreamSynchronize(s->stream);
   cudaFree(s->ghost), cudaFree(s->ghost_off);
   cudaFree(s->slots), cudaFree(s->flags), cudaFree(s->seq);
   cudaFree(s->hflags), cudaFree(s->send_idx), cudaFree(s->push_ticket);
+  lap("free rest");
   if (s->bounce[0]) cudaFreeHost(s->bounce[0]);
   if (s->bounce[1]) cudaFreeHost(s->bounce[1]);
+  lap("free bounce");
   if (s->stream2) cudaStreamDestroy(s->stream2);
   cudaFreeHost(s->h_H), cudaFreeHost(s->h_scale), cudaFreeHost(s->h_ctl);
   cudaFreeHost(s->h_step_round2), cudaFreeHost(s->h_q);
   if (s->stream) cudaStreamDestroy(s->stream);
+  lap("host+stream");
   delete s;
   return AB200_OK;
 }
@@ -502,8 +543,17 @@ int ab200_create(ab200_solver** out, int device, int64_t n_global, int64_t row0,
     }                                               \
   } while (0)
   CUX(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-  CUX(cudaMalloc(&s->V, sizeof(cplx) * (size_t)s->ld * md1));
-  CUX(cudaMalloc(&s->wtmp, sizeof(cplx) * (size_t)s->ld));
+  if (nrows_local == n_global) {
+    cudaMemPool_t pool = nullptr;
+    unsigned long long keep = ~0ull;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess &&
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep) == cudaSuccess)
+      s->pooled = true;
+    else
+      cudaGetLastError();
+  }
+  CUX(big_alloc(s, &s->V, sizeof(cplx) * (size_t)s->ld * md1));
+  CUX(big_alloc(s, &s->wtmp, sizeof(cplx) * (size_t)s->ld));
   CUX(cudaMalloc(&s->scale, sizeof(double) * md1));
   CUX(cudaMalloc(&s->Hdev, sizeof(cplx) * (size_t)md1 * max_dim));
   CUX(cudaMalloc(&s->hscratch, sizeof(cplx) * (md1 + 1)));
@@ -557,16 +607,16 @@ int ab200_set_csr(ab200_solver* s, const void* indptr, int indptr_bits, const in
     int rc = switch_to_complex(s);
     if (rc != AB200_OK) return rc;
   }
-  cudaFree(s->indptr), cudaFree(s->indices), cudaFree(s->values), cudaFree(s->rowblk);
+  big_free(s, s->indptr), big_free(s, s->indices), big_free(s, s->values), cudaFree(s->rowblk);
   s->indptr = s->indices = nullptr, s->values = nullptr, s->rowblk = nullptr;
   s->nnz = -1;
   s->op_fn = nullptr;
   const size_t ipb = (size_t)indptr_bits / 8, vb = value_kind == AB200_F64 ? 8 : 16;
   // spare entries: the SpMV stages whole 16-byte groups (4 column ids / values, 4 or 2 row
   // pointers), so every array may be read a little past its end
-  CU(cudaMalloc(&s->indptr, ipb * (s->n + 1 + 8)));
-  CU(cudaMalloc(&s->indices, sizeof(int32_t) * (size_t)(nnz + 8)));
-  CU(cudaMalloc(&s->values, vb * (size_t)(nnz + 8)));
+  CU(big_alloc(s, &s->indptr, ipb * (s->n + 1 + 8)));
+  CU(big_alloc(s, &s->indices, sizeof(int32_t) * (size_t)(nnz + 8)));
+  CU(big_alloc(s, &s->values, vb * (size_t)(nnz + 8)));
   CU(cudaMemsetAsync(static_cast<char*>(s->indptr) + ipb * (s->n + 1), 0, ipb * 8, s->stream));
   CU(cudaMemsetAsync(s->indices + nnz, 0, sizeof(int32_t) * 8, s->stream));
   CU(cudaMemsetAsync(static_cast<char*>(s->values) + vb * (size_t)nnz, 0, vb * 8, s->stream));
@@ -671,7 +721,7 @@ int ab200_set_operator(ab200_solver* s, ab200_apply_fn fn, void* user, int value
     int rc = switch_to_complex(s);
     if (rc != AB200_OK) return rc;
   }
-  if (!s->xtmp) CU(cudaMalloc(&s->xtmp, sizeof(cplx) * (size_t)s->ld));
+  if (!s->xtmp) CU(big_alloc(s, &s->xtmp, sizeof(cplx) * (size_t)s->ld));
   s->op_fn = fn;
   s->op_user = user;
   s->value_kind = value_kind;
@@ -1172,7 +1222,7 @@ int ab200_spmv(ab200_solver* s, const double* x_host, double* y_host) {
     return set_err(AB200_ESTATE, "ab200_spmv is a single-GPU entry point (row block is partial)");
   CU(cudaSetDevice(s->device));
   break_chain(s);
-  if (!s->xtmp) CU(cudaMalloc(&s->xtmp, sizeof(cplx) * (size_t)s->ld));
+  if (!s->xtmp) CU(big_alloc(s, &s->xtmp, sizeof(cplx) * (size_t)s->ld));
   // a real x on a real operator takes the float64 kernels, exactly as inside a real-storage
   // expansion (the complex result has zero imaginary parts either way)
   bool real = s->real_mode && s->value_kind == AB200_F64 && s->op_fn == nullptr;
@@ -1256,6 +1306,8 @@ static const int kSlotDoubles = 2 * 129 + 8;
 
 int ab200_comm_export(ab200_solver* s, void* blob) {
   REQUIRE(s != nullptr && blob != nullptr, "null argument");
+  if (s->pooled)
+    return set_err(AB200_ESTATE, "this solver owns the whole operator (nrows_local == n_global): nothing to share");
   CU(cudaSetDevice(s->device));
   break_chain(s);
   if (!s->slots) {

@@ -80,23 +80,67 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clock / throttle-reason samples during the timed region."""
+    """SM clock / throttle-reason samples during the timed region, time-stamped; `stop(t0, t1)`
+    keeps the samples taken inside [t0, t1] (perf_counter).
+
+    Source: NVML (nvidia_ml_py -- the library behind nvidia-smi; same fields as the recipe's
+    `nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.*` line), polled every
+    5 ms from a thread.  A looping `nvidia-smi -lms` child is the fallback; it needs a few hundred
+    milliseconds before its first line while the timed region lasts 75 ms at 8 GPUs, so the
+    sampler is started before the warm-up cycles either way."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index=0):
         self.index = index
         self.proc = None
-        self.lines = []
+        self.samples = []      # (t, sm_mhz, max_mhz, {reasons})
+        self.source = None
+        self._stop = False
+
+    # -- NVML
+    def _nvml_loop(self, nv, handle):
+        bits = [(nv.nvmlClocksEventReasonHwSlowdown, "hw_slowdown"),
+                (nv.nvmlClocksEventReasonHwThermalSlowdown, "hw_thermal_slowdown"),
+                (nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_thermal_slowdown"),
+                (nv.nvmlClocksEventReasonSwPowerCap, "sw_power_cap")]
+        mx = float(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM))
+        while not self._stop:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM))
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(handle))
+                self.samples.append((time.perf_counter(), sm, mx, {n for b, n in bits if mask & b}))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
         try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if vis:      # CUDA ordinal -> physical index
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if idx < len(ids) and ids[idx].isdigit():
+                    idx = int(ids[idx])
+            handle = nv.nvmlDeviceGetHandleByIndex(idx)
+            nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)
+            self.source = "nvml"
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, handle), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            pass
+        try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi -lms 50"
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except Exception:
@@ -104,33 +148,42 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
-
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
             f = [x.strip() for x in line.split(",")]
             if len(f) < 6:
                 continue
             try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
+                sm, mx = float(f[0]), float(f[1])
             except ValueError:
                 continue
-            for name, v in zip(names, f[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None,
-                "sm_max_mhz": float(np.max(mx)) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+            rs = {n for n, v in zip(self.NAMES, f[2:6]) if v.lower().startswith("active")}
+            self.samples.append((time.perf_counter(), sm, mx, rs))
+
+    def stop(self, t0=None, t1=None):
+        self._stop = True
+        if self.source is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["no NVML, no nvidia-smi"]}
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        else:
+            self.thread.join(timeout=1.0)
+        inside = [x for x in self.samples if t0 is None or (t0 <= x[0] <= t1)]
+        window = "timed region"
+        if not inside and t0 is not None:
+            # a region shorter than the polling period: the samples under the same load right
+            # around it (the warm-up cycles before, the un-instrumented cycles after)
+            inside = [x for x in self.samples if t0 - 0.25 <= x[0] <= t1 + 0.25]
+            window = "timed region +- 0.25 s (same load: warm-up cycles before, re-run after)"
+        reasons = set()
+        for x in inside:
+            reasons |= x[3]
+        return {"sm_mhz": float(np.median([x[1] for x in inside])) if inside else None,
+                "sm_max_mhz": float(max(x[2] for x in inside)) if inside else None,
+                "samples": len(inside), "window": window, "source": self.source,
+                "reasons": sorted(reasons)}
 
 
 def set_host_threads():
@@ -420,13 +473,42 @@ def converged_leg(cpu, comm=None, device=0):
 
 
 # ----------------------------------------------------------------------------- GPU arm
-def kernel_table(st, ms, peak):
+def warm_for_sampler(cycle, comm, seconds=1.0, cap=400):
+    """Extra warm-up cycles, the same number on every rank, so that the nvidia-smi sampler
+    (started before the warm-up) is delivering lines under load when the timed region starts."""
+    t0 = time.perf_counter()
+    cycle()
+    dt = time.perf_counter() - t0
+    if comm is not None:
+        dt = comm.max_float(dt)
+    n = int(min(cap, max(0, np.ceil(seconds / max(dt, 1e-4)))))
+    for _ in range(n):
+        cycle()
+    return n + 1
+
+
+def event_note(steps):
+    idx = list(range(0, steps, EVENT_EVERY))
+    return (f"CUDA events around every launch of cycles {idx} of the {steps}-cycle timed region "
+            f"(every {EVENT_EVERY}th cycle: an event record between two kernels costs the device "
+            "~3 us, 0.36 ms per cycle -- 4% of a cycle at 8 GPUs; tools/event_cost.py); "
+            "per-class launches / bytes are those of the instrumented cycles")
+
+
+EVENT_EVERY = 4      # cycles 0, 4, 8, ... of the timed region carry the per-kernel CUDA events
+
+
+def kernel_table(st, ms, peak, frac=1.0):
+    """Per-class figures from the launches that carried CUDA events: `frac` of the timed
+    region's cycles (every cycle launches the same kernels, so launches and bytes scale by it);
+    `ms` = duration of those instrumented cycles."""
     classes = {}
     for key in ("spmv", "ortho_pass1", "ortho_fused", "ortho_pass2", "restart"):
         if st[key + "_launches"] and st[key + "_ms"] > 0:
-            classes[key] = dict(ms=st[key + "_ms"], bytes=st[key + "_bytes"],
-                                launches=st[key + "_launches"],
-                                gbs=st[key + "_bytes"] / st[key + "_ms"] / 1e6)
+            launches = int(round(st[key + "_launches"] * frac))
+            nbytes = st[key + "_bytes"] * frac
+            classes[key] = dict(ms=st[key + "_ms"], bytes=nbytes, launches=launches,
+                                gbs=nbytes / st[key + "_ms"] / 1e6)
     top = max(classes, key=lambda k: classes[k]["ms"])
     kernels = {k: {"launches": v["launches"], "avg_ms": v["ms"] / v["launches"],
                    "achieved_gbs": v["gbs"], "frac_of_measured": v["gbs"] / peak,
@@ -489,41 +571,51 @@ def run_b200(args):
         grow(P)
 
     grow(0)
+    clocks = ClockSampler(local)
+    clocks.start()
     for _ in range(max(3, args.warmup)):
         cycle()
+    extra = warm_for_sampler(cycle, None)
     dev.synchronize()
     dev.reset_stats()
     host_ms.clear()
-    clocks = ClockSampler(local)
-    clocks.start()
+    cyc_s = []
     dev.timer_start()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        cycle()
+    for i in range(args.steps):
+        dev.set_timing(i % EVENT_EVERY == 0)
+        tc = time.perf_counter()
+        cycle()                      # ends with a stream synchronise: the host clock brackets it
+        cyc_s.append(time.perf_counter() - tc)
     ms = dev.timer_stop()
-    wall = time.perf_counter() - t0
-    clk = clocks.stop()
+    t1 = time.perf_counter()
+    wall = t1 - t0
     st = dev.stats()
     matvecs = args.steps * (MAX_DIM - P)
     assert st["arnoldi_steps"] == matvecs, (st["arnoldi_steps"], matvecs)
     value = matvecs / (ms * 1e-3)
-    # the same cycles without the per-kernel CUDA events (one event record sits between every
-    # two kernels of the timed region above): what the instrumentation costs, reported beside it
+    timed_cycles = len(range(0, args.steps, EVENT_EVERY))
+    ms_instr = 1e3 * sum(cyc_s[0::EVENT_EVERY])
+    # the same cycles without any per-kernel CUDA events, reported beside the timed region
     dev.set_timing(False)
     dev.timer_start()
     for _ in range(args.steps):
         cycle()
     ms_plain = dev.timer_stop()
+    clk = clocks.stop(t0, t1)
+    clk["warmup_extra_cycles"] = extra
 
     # ---- roofline of the dominant kernel class (CUDA events inside the timed region)
     peak, peak_src = measured_peak()
-    classes, top, kernels = kernel_table(st, ms, peak)
+    classes, top, kernels = kernel_table(st, ms_instr, peak, timed_cycles / args.steps)
     roofline = {"bound": "hbm", "kernel": top, "achieved": classes[top]["gbs"], "peak": peak,
                 "unit": "GB/s", "frac": classes[top]["gbs"] / peak, "peak_source": peak_src,
                 "traffic": traffic_from_profile(top, grid, st, classes[top]["bytes"] / classes[top]["launches"]),
                 "algorithmic_bytes_per_launch": classes[top]["bytes"] / classes[top]["launches"],
+                "kernel_events": event_note(args.steps),
                 "kernels": kernels,
-                "kernel_sum_ms_per_step": sum(v["ms"] for v in classes.values()) / args.steps,
+                "kernel_sum_ms_per_step": sum(v["ms"] for v in classes.values()) / timed_cycles,
+                "ms_per_instrumented_step": ms_instr / timed_cycles,
                 "host_rotate_ms_per_step": float(np.mean(host_ms[:args.steps])),
                 "ms_per_step_without_kernel_events": ms_plain / args.steps,
                 "dgks_second_round_fraction": st["second_rounds"] / max(1, st["arnoldi_steps"])}
@@ -670,41 +762,53 @@ def run_b200_multi(args, rank, world, local):
         grow(P)
 
     grow(0)
-    for _ in range(max(3, args.warmup)):
-        cycle()
-    dev.synchronize()
-    dev.reset_stats()
-    host_ms.clear()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+    for _ in range(max(3, args.warmup)):
+        cycle()
+    extra = warm_for_sampler(cycle, comm)
+    dev.synchronize()
+    dev.reset_stats()
+    host_ms.clear()
+    cyc_s = []
     comm.barrier()
     dev.timer_start()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for i in range(args.steps):
+        dev.set_timing(i % EVENT_EVERY == 0)
+        tc = time.perf_counter()
         cycle()
+        cyc_s.append(time.perf_counter() - tc)
     ms = dev.timer_stop()
-    wall = time.perf_counter() - t0
+    t1 = time.perf_counter()
+    wall = t1 - t0
     comm.barrier()
-    clk = clocks.stop() if rank == 0 else None
     ms_max = comm.max_float(ms)
     wall_max = comm.max_float(wall)
     st = dev.stats()
     matvecs = args.steps * (MAX_DIM - P)
     value = matvecs / (ms_max * 1e-3)
-    # the same cycles without the per-kernel CUDA events (see run_b200)
+    timed_cycles = len(range(0, args.steps, EVENT_EVERY))
+    ms_instr = 1e3 * sum(cyc_s[0::EVENT_EVERY])
+    # the same cycles without any per-kernel CUDA events (see run_b200)
     dev.set_timing(False)
     comm.barrier()
     dev.timer_start()
     for _ in range(args.steps):
         cycle()
     ms_plain = comm.max_float(dev.timer_stop())
+    clk = clocks.stop(t0, t1) if rank == 0 else None
+    if clk is not None:
+        clk["warmup_extra_cycles"] = extra
     peak, peak_src = measured_peak()
-    classes, top, kernels = kernel_table(st, ms, peak)
+    classes, top, kernels = kernel_table(st, ms_instr, peak, timed_cycles / args.steps)
     roofline = {"bound": "hbm", "kernel": top, "achieved": classes[top]["gbs"], "peak": peak,
                 "unit": "GB/s", "frac": classes[top]["gbs"] / peak, "peak_source": peak_src,
-                "traffic": None, "kernels": kernels, "note": "rank 0, per-GPU bytes / per-GPU time",
-                "kernel_sum_ms_per_step": sum(v["ms"] for v in classes.values()) / args.steps,
+                "traffic": None, "kernel_events": event_note(args.steps),
+                "kernels": kernels, "note": "rank 0, per-GPU bytes / per-GPU time",
+                "kernel_sum_ms_per_step": sum(v["ms"] for v in classes.values()) / timed_cycles,
+                "ms_per_instrumented_step": ms_instr / timed_cycles,
                 "host_rotate_ms_per_step": float(np.mean(host_ms[:args.steps])),
                 "ms_per_step_without_kernel_events": ms_plain / args.steps,
                 "halo_entries_rank0": int(len(plan.ghost_cols))}
