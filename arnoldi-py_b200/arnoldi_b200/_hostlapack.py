@@ -31,18 +31,37 @@ def _capsule_pointer(name):
     return C.c_void_p(ptr)
 
 
+# max |H - H^T| / max |H| below which a real H_m is treated as symmetric (fast_real_schur only)
+SYM_TOL = 1e-12
+
+
 class NativeRotate:
     def __init__(self):
         self.lib = _lib.load()
         self.zgees = _capsule_pointer("zgees")
         self.ztrexc = _capsule_pointer("ztrexc")
         self.dgees = _capsule_pointer("dgees")
+        try:
+            self.dsyevd = _capsule_pointer("dsyevd")
+        except Exception:
+            self.dsyevd = None
 
     def __call__(self, Hm, sort_function, real_ok=False):
         m = Hm.shape[0]
         T = np.array(Hm, dtype=np.complex128, order="F", copy=True)
         Q = np.empty((m, m), np.complex128, order="F")
         if real_ok and not np.any(T.imag):
+            if self.dsyevd is not None:
+                # symmetric H_m (symmetric operator): eigendecomposition, ordered by a permutation
+                info = self.lib.ab200_host_eigh_real(self.dsyevd, m, T.ctypes.data_as(C.c_void_p),
+                                                     Q.ctypes.data_as(C.c_void_p), SYM_TOL)
+                if info == 0:
+                    perm = np.ascontiguousarray(sort_function(np.diag(T)), dtype=np.int64)
+                    assert perm.shape == (m,), "sort_function must return a permutation of all m indices"
+                    return (np.asfortranarray(np.diag(np.diag(T)[perm])),
+                            np.asfortranarray(Q[:, perm]))
+                if info != 1:
+                    raise np.linalg.LinAlgError(f"dsyevd failed with info = {info}")
             info = self.lib.ab200_host_schur_real(self.dgees, m, T.ctypes.data_as(C.c_void_p),
                                                   Q.ctypes.data_as(C.c_void_p))
             if info != 0:

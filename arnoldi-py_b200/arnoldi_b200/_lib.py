@@ -84,6 +84,7 @@ SIGNATURES = {
     "ab200_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
     "ab200_host_schur": (C.c_int, [_P, C.c_int, _P, _P, _P]),
     "ab200_host_schur_real": (C.c_int, [_P, C.c_int, _P, _P]),
+    "ab200_host_eigh_real": (C.c_int, [_P, C.c_int, _P, _P, C.c_double]),
     "ab200_host_reorder": (C.c_int, [_P, C.c_int, _P, _P, _P, _P]),
     "ab200_host_alloc": (C.c_int, [C.POINTER(_P), C.c_int64]),
     "ab200_host_free": (C.c_int, [_P]),

@@ -125,9 +125,11 @@ def partial_schur(
         (ARPACK's adjustment); the reference keeps ``p`` (README.md:117 lists this as TODO).
     fast_real_schur : True factors H_m with dgees + 2 x 2 block rotations instead of zgees while
         H_m is real (real basis): a third of the host arithmetic of a restart, which is what the
-        GPUs wait for.  A valid ordered Schur form, but not the reference's bit for bit (signs /
-        phases of the Schur vectors, rounding): converged values agree, restart counts may move
-        by rounding noise exactly as they do between OpenBLAS builds.
+        GPUs wait for; a real H_m that is symmetric to 1e-12 (a symmetric operator) is
+        eigendecomposed with dsyevd instead and ordered by a column permutation.  A valid ordered
+        Schur form, but not the reference's bit for bit (signs / phases of the Schur vectors,
+        rounding): converged values agree, restart counts may move by rounding noise exactly as
+        they do between OpenBLAS builds.
     halo  : "pull" (each rank reads the remote entries of v it needs straight from peer HBM),
         "push" (the owner gathers locally and streams them into the peer's buffer) or "auto"
         (push when some rank's halo has more than 65 536 scattered entries)

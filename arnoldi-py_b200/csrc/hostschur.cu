@@ -30,6 +30,8 @@ typedef void (*ztrexc_t)(char* compq, int* n, zc* t, int* ldt, zc* q, int* ldq, 
 typedef void (*dgees_t)(char* jobvs, char* sort, void* select, int* n, double* a, int* lda,
                         int* sdim, double* wr, double* wi, double* vs, int* ldvs, double* work,
                         int* lwork, int* bwork, int* info);
+typedef void (*dsyevd_t)(char* jobz, char* uplo, int* n, double* a, int* lda, double* w, double* work,
+                         int* lwork, int* iwork, int* liwork, int* info);
 
 thread_local std::vector<double> g_da, g_dvs, g_dwork, g_wr, g_wi;
 thread_local std::vector<zc> g_work;
@@ -144,6 +146,53 @@ int ab200_host_schur_real(void* dgees_fn, int m, double* t, double* q) {
     }
     at(T, k, k - 1).re = 0.0, at(T, k, k - 1).im = 0.0;
   }
+  return 0;
+}
+
+// Schur form of a real SYMMETRIC matrix = its eigendecomposition: dsyevd on (H + H^T) / 2, a
+// quarter of dgees's time at m = 40, and the ordered form is then a permutation of the columns
+// (no ztrexc moves).  The projected matrix of a symmetric operator is symmetric up to the
+// rounding of the orthogonalisation coefficients; the routine measures max |H - H^T| and
+// declines (returns 1, nothing written) when it exceeds sym_tol * max |H| -- the caller then
+// takes ab200_host_schur_real.  On success T is diagonal (ascending) and Q real orthogonal, both
+// written as complex column-major m x m.  Like ab200_host_schur_real this is a valid Schur form
+// of H to within sym_tol, not the reference's bit for bit.
+int ab200_host_eigh_real(void* dsyevd_fn, int m, double* t, double* q, double sym_tol) {
+  if (dsyevd_fn == nullptr || t == nullptr || q == nullptr || m < 1 || !(sym_tol >= 0.0)) return AB200_EINVAL;
+  dsyevd_t dsyevd = reinterpret_cast<dsyevd_t>(dsyevd_fn);
+  const size_t mm = (size_t)m * m;
+  double hmax = 0.0, asym = 0.0;
+  for (int c = 0; c < m; ++c)
+    for (int r = 0; r < m; ++r) {
+      const size_t i = (size_t)c * m + r, j = (size_t)r * m + c;
+      if (t[2 * i + 1] != 0.0) return AB200_EINVAL;
+      const double a = fabs(t[2 * i]), d = fabs(t[2 * i] - t[2 * j]);
+      hmax = a > hmax ? a : hmax;
+      asym = d > asym ? d : asym;
+    }
+  if (asym > sym_tol * hmax) return 1;
+  g_da.resize(mm);
+  g_wr.resize(m);
+  for (int c = 0; c < m; ++c)
+    for (int r = 0; r < m; ++r)
+      g_da[(size_t)c * m + r] = 0.5 * (t[2 * ((size_t)c * m + r)] + t[2 * ((size_t)r * m + c)]);
+  char jobz = 'V', uplo = 'L';
+  int n = m, lda = m, info = 0, lwork = -1, liwork = -1, iquery = 0;
+  double query = 0.0;
+  dsyevd(&jobz, &uplo, &n, g_da.data(), &lda, g_wr.data(), &query, &lwork, &iquery, &liwork, &info);
+  if (info != 0) return info < 0 ? AB200_EINVAL : info + 1;
+  lwork = (int)query;
+  liwork = iquery;
+  if (lwork < 1 + 6 * m + 2 * m * m) lwork = 1 + 6 * m + 2 * m * m;
+  if (liwork < 3 + 5 * m) liwork = 3 + 5 * m;
+  if ((int)g_dwork.size() < lwork) g_dwork.resize(lwork);
+  std::vector<int> iwork(liwork);
+  dsyevd(&jobz, &uplo, &n, g_da.data(), &lda, g_wr.data(), g_dwork.data(), &lwork, iwork.data(), &liwork,
+         &info);
+  if (info != 0) return info < 0 ? AB200_EINVAL : info + 1;
+  memset(t, 0, sizeof(double) * 2 * mm);
+  for (int i = 0; i < m; ++i) t[2 * ((size_t)i * m + i)] = g_wr[i];
+  for (size_t i = 0; i < mm; ++i) q[2 * i] = g_da[i], q[2 * i + 1] = 0.0;
   return 0;
 }
 

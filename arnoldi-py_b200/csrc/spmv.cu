@@ -1,23 +1,23 @@
-// spmv.cu -- CSR sparse matrix x complex128 vector  (the reference's `A @ V[:, j]`,
-// decomposition.py:57-58, which lands in scipy's csr_matvec).
+// spmv.cu -- CSR sparse matrix x vector  (the reference's `A @ V[:, j]`, decomposition.py:57-58,
+// which lands in scipy's csr_matvec).  Values float64 or complex128; vectors complex128, or
+// float64 while the basis is stored real.
 //
-// Work decomposition ("nnz tiles with row-aligned edges"):
-//   * the nnz range is cut into tiles of `tile` entries; tile b starts at the first
-//     row whose indptr >= b * tile (rowblk[], built once per matrix on the device),
-//     so every block owns whole rows and about the same number of non-zeros no
-//     matter how skewed the row lengths are (the merge-path idea, with the split
-//     snapped to row boundaries);
-//   * a block stages its tile of values + column ids into shared memory with
-//     coalesced 128-bit loads, then one thread per row walks its segment in STORED
-//     ORDER with separate multiply and add -- the same operation order as scipy's
-//     csr_matvec, so for rows handled this way y is bit-identical to scipy;
-//   * a row whose part of the tile is longer than kShortRow (16) entries is summed by a whole
-//     warp instead (lanes stride the segment, fixed-order butterfly: deterministic, but not
-//     scipy's order), and a row longer than a tile is carried across the block's tile
-//     iterations through y.  Without this, one thread walking a 100-entry row serialises
-//     the block on power-law matrices.
-// x is gathered with 128-bit read-only loads; for banded matrices consecutive rows
-// gather consecutive x entries, so the gathers coalesce and hit L2.
+// Work decomposition, common to every kernel here ("nnz tiles with row-aligned edges"): the nnz
+// range is cut into tiles of `tile` entries; tile b starts at the first row whose indptr >=
+// b * tile (rowblk[], built once per matrix on the device), so every tile owns whole rows and
+// about the same number of non-zeros no matter how skewed the row lengths are (the merge-path
+// split, snapped to row boundaries).  Rows are summed in STORED ORDER with separate multiply and
+// add -- the operation order of scipy's csr_matvec -- wherever one thread sums a row, so those
+// rows are bit-identical to scipy.
+//
+//   spmv_bulk_kernel    rows of <= 16 entries (mark, the Laplacians): a producer warp moves each
+//                       tile into a shared-memory ring with bulk copies (TMA) + mbarriers, one
+//                       consumer thread per row.  The default for such operators.
+//   spmv_stream_kernel  the same with cp.async staging and block barriers (round 1; A/B only).
+//   spmv_ring_kernel    skewed rows, float64 vectors: one warp per tile, x gathered from a
+//                       shared-memory ring that slides along the diagonal.
+//   spmv_tile_kernel    everything else: one block per tile, x gathered from global memory, a
+//                       warp for segments > 16 entries, rows longer than a tile carried through y.
 #include "kernels.cuh"
 
 namespace ab200 {

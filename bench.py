@@ -377,8 +377,10 @@ def workload_config(grid=GRID_FULL):
                     f"truncation V[:, :{P}] = V Q, expansion {P}->{MAX_DIM} "
                     f"({MAX_DIM-P} SpMV + CGS2/DGKS)",
             "l2": "inputs larger than L2 (V = 11.0 GB, A = 1.07 GB)",
-            "host_schur_b200_arm": ("dgees + 2x2 block rotations while H is real "
-                                    "(fast_real_schur=True); the reference arm runs its own zgees"),
+            "host_schur_b200_arm": ("fast_real_schur=True: while H is real, dsyevd + a column "
+                                    "permutation when H is symmetric to 1e-12 (this operator), "
+                                    "else dgees + 2x2 block rotations; the reference arm runs its "
+                                    "own zgees + ztrexc"),
             "ritz_parity_note": "this operator has double eigenvalues: its Ritz-value parity is "
                                 "pinned at N <= 64 and by eigenvalue membership + residual beyond; "
                                 "the `parity` block is on operators with simple spectra"}

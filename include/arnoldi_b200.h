@@ -260,6 +260,12 @@ int ab200_host_schur(void *zgees_fn, int m, double *t, double *q, double *work);
  * returns (order of the diagonal before sorting, phases, rounding): used where the driver
  * leaves the reference's arithmetic anyway (see `fast_real_schur` in INTEGRATION.md). */
 int ab200_host_schur_real(void *dgees_fn, int m, double *t, double *q);
+/* Real SYMMETRIC H_m (the projected matrix of a symmetric operator): eigendecomposition by dsyevd
+ * on (H + H^T) / 2 -- T diagonal (ascending), Q real orthogonal, both written as complex m x m;
+ * the ordered form is then a column permutation (no ztrexc).  Returns 1 without writing anything
+ * when max |H - H^T| > sym_tol * max |H| (take ab200_host_schur_real then), 0 on success.  Like
+ * ab200_host_schur_real: opt-in (fast_real_schur), a valid Schur form, not the reference's bits. */
+int ab200_host_eigh_real(void *dsyevd_fn, int m, double *t, double *q, double sym_tol);
 int ab200_host_reorder(void *ztrexc_fn, int m, double *t, double *q, const int64_t *perm,
                        double *work);
 

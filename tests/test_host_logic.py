@@ -248,3 +248,43 @@ def test_reference_import_names_resolve_to_the_device_path():
     assert all(callable(f) for f in (arnoldi_decomposition, dgks_gs, dgks_mgs, arg_largest_real,
                                      ordered_schur))
     assert "arnoldi-py_b200" in arnoldi.__file__
+
+
+def test_fast_real_rotate_paths():
+    """fast_real_schur's host rotate: a real symmetric H_m (what a symmetric operator projects
+    to, up to rounding) takes dsyevd + a column permutation, a real nonsymmetric one dgees + 2 x 2
+    rotations, anything else zgees.  Every path returns an ordered Schur form of H: unitary Q,
+    upper-triangular T with the diagonal in the order sort_function asks for, H Q = Q T; the
+    eigenvalues agree with the reference's zgees path to rounding."""
+    from arnoldi_b200.rotate import rotate
+    from arnoldi_b200.utils import arg_largest_magnitude, arg_largest_real
+    rng = np.random.default_rng(21)
+    for trial in range(30):
+        m = int(rng.integers(3, 64))
+        p = int(rng.integers(1, m - 1))
+        d, e, s = rng.standard_normal(m), rng.standard_normal(m - 1), 1e-3 * rng.standard_normal(p)
+        H = np.diag(d) + np.diag(e, 1) + np.diag(e, -1)      # Krylov-Schur shape: diagonal block,
+        H[:p, :p] = np.diag(d[:p])                            # spike row / column, tridiagonal rest
+        H[p, :p] = s
+        H[:p, p] = s
+        kind = trial % 3
+        if kind == 0:      # symmetric up to rounding noise
+            H = H + 1e-15 * np.triu(rng.standard_normal((m, m)), 1)
+        elif kind == 1:    # real, clearly nonsymmetric
+            H = H + np.triu(rng.standard_normal((m, m)), 1)
+        else:              # complex
+            H = H + 1j * np.triu(rng.standard_normal((m, m)), 0)
+        H = H.astype(np.complex128)
+        for sort in (arg_largest_real, arg_largest_magnitude):
+            T0, Q0 = rotate(H, sort, fast_real=False)
+            T, Q = rotate(H, sort, fast_real=True)
+            scale = np.abs(H).max()
+            assert np.abs(Q.conj().T @ Q - np.eye(m)).max() < 1e-13
+            assert np.abs(np.tril(T, -1)).max() == 0.0
+            assert np.abs(H @ Q - Q @ T).max() < 1e-12 * scale * m
+            np.testing.assert_array_equal(np.diag(T)[sort(np.diag(T))], np.diag(T))
+            if kind == 0:
+                assert np.abs(np.triu(T, 1)).max() == 0.0 and not np.any(Q.imag)      # dsyevd path
+                np.testing.assert_allclose(np.diag(T), np.diag(T0), rtol=0, atol=1e-12 * scale)
+            if kind == 2:
+                np.testing.assert_array_equal(T, T0)                                   # zgees both ways
