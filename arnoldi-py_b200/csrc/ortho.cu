@@ -552,27 +552,33 @@ __global__ void __launch_bounds__(CT < 5 ? 256 : 512) cgs_fused_kernel(OrthoArgs
       mine[r * kWarp + lane] = t;
     }
     __syncthreads();  // partial sums (and, PF, warp 0's chunk of w) visible to the block
-    // ONE warp (rotating with the chunk, so the work spreads evenly) rebuilds w' for the
-    // chunk, stores it and publishes it through shared memory; the others only read it back.
-    // (Every warp doing the W-term sum itself saturated the shared-memory pipe.)
-    if (warp == (int)(iter % nwarps)) {
-      if (PF) {
-#pragma unroll
-        for (int r = 0; r < R; ++r) wv[r] = sw[(size_t)slot * ROWS + r * kWarp + lane];
-      }
+    // w' of the chunk is rebuilt by the first ROWS threads of the block, one element each (so
+    // two or more warps share what used to be one warp's serial section between the barriers),
+    // stored, and published through shared memory; everybody reads it back.  The W partial sums
+    // of an element are added in warp order, as before.  (Every warp doing the W-term sum for
+    // all ROWS elements itself saturated the shared-memory pipe.)
+    {
       const cplx* all = spart + (size_t)buf * nwarps * ROWS;
+      for (int e = threadIdx.x; e < ROWS; e += blockDim.x) {
+        cplx win;
+        if (PF) {
+          win = sw[(size_t)slot * ROWS + e];
+        } else {
+          win = wv[0];   // element e = r * 32 + lane sits in this thread's own wv[r]
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
+          for (int r = 1; r < R; ++r)
+            if ((e >> 5) == r) win = wv[r];
+        }
         cplx t = make_double2(0.0, 0.0);
-        for (int k2 = 0; k2 < nwarps; ++k2) t = cadd(t, all[k2 * ROWS + r * kWarp + lane]);
-        wv[r].x -= t.x;
-        wv[r].y -= t.y;
-        swp[r * kWarp + lane] = wv[r];
-        const bool ok = full || base + r * kWarp < a.n;
-        if (ok) {
-          st_stream(w + base + r * kWarp, wv[r]);
-          nacc = fma(wv[r].x, wv[r].x, nacc);
-          nacc = fma(wv[r].y, wv[r].y, nacc);
+        for (int k2 = 0; k2 < nwarps; ++k2) t = cadd(t, all[k2 * ROWS + e]);
+        win.x -= t.x;
+        win.y -= t.y;
+        swp[e] = win;
+        const int64_t row = q * ROWS + e;
+        if (row < a.n) {
+          st_stream(w + row, win);
+          nacc = fma(win.x, win.x, nacc);
+          nacc = fma(win.y, win.y, nacc);
         }
       }
     }
