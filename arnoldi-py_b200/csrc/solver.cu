@@ -93,6 +93,8 @@ struct ab200_solver {
   int value_kind = AB200_F64;
   int64_t nnz = -1;
   int64_t* rowblk = nullptr;
+  int64_t* rowblk_ring = nullptr;   // second tiling (short tiles, one per warp) for the ring kernels
+  int tile_ring = 0, nblk_ring = 0;
   int nblk = 0;
   int tile = 0;
   int spmv_threads = 128;
@@ -483,6 +485,7 @@ int ab200_destroy(ab200_solver* s) {
   cudaFree(s->hscratch), cudaFree(s->coef), cudaFree(s->part), cudaFree(s->npart);
   cudaFree(s->ticket), cudaFree(s->ctl), cudaFree(s->step_round2), cudaFree(s->qdev);
   big_free(s, s->indptr), big_free(s, s->indices), big_free(s, s->values), cudaFree(s->rowblk);
+  cudaFree(s->rowblk_ring);
   if (s->pooled && s->stream) cudaStreamSynchronize(s->stream);
   cudaFree(s->ghost), cudaFree(s->ghost_off);
   cudaFree(s->slots), cudaFree(s->flags), cudaFree(s->seq);
@@ -608,7 +611,9 @@ int ab200_set_csr(ab200_solver* s, const void* indptr, int indptr_bits, const in
     if (rc != AB200_OK) return rc;
   }
   big_free(s, s->indptr), big_free(s, s->indices), big_free(s, s->values), cudaFree(s->rowblk);
-  s->indptr = s->indices = nullptr, s->values = nullptr, s->rowblk = nullptr;
+  cudaFree(s->rowblk_ring);
+  s->indptr = s->indices = nullptr, s->values = nullptr, s->rowblk = nullptr, s->rowblk_ring = nullptr;
+  s->tile_ring = s->nblk_ring = 0;
   s->nnz = -1;
   s->op_fn = nullptr;
   const size_t ipb = (size_t)indptr_bits / 8, vb = value_kind == AB200_F64 ? 8 : 16;
@@ -659,10 +664,11 @@ int ab200_set_csr(ab200_solver* s, const void* indptr, int indptr_bits, const in
   s->spmv_window = 0;
   s->spmv_locality_pm = 0;
   if (!short_rows && spmv_algo != AB200_SPMV_VECTOR && nnz > 0) {
-    // ring capacity in x entries.  8192 (64 KB) measured best on the power-law operator: it holds
-    // +-3328 entries around a round's rows and leaves ~90 KB of L1 to the gathers that miss it
-    // (16384 entries: 1.00 ms, 8192: 0.92 ms at n = 1e7)
-    int wcap = s->opt_spmv_window > 0 ? s->opt_spmv_window : 8192;
+    // ring capacity in x entries (float64).  The cp.async kernel (default) takes what its 31 strip
+    // buffers leave of the shared memory (~11 000 entries: +-4.7 k around a round's rows); the
+    // register-staged kernel (spmv_variant = 4) measured best with 8192, which leaves ~90 KB of
+    // L1 to the gathers that miss the ring (profiles/r02_spmv_ring.md)
+    int wcap = s->opt_spmv_window > 0 ? s->opt_spmv_window : (s->opt_spmv_variant == 4 ? 8192 : 11008);
     if (wcap < 256) wcap = 256;
     if (wcap > 16384) wcap = 16384;
     wcap = wcap / 256 * 256;
@@ -682,8 +688,14 @@ int ab200_set_csr(ab200_solver* s, const void* indptr, int indptr_bits, const in
       s->spmv_window = 1;
       s->spmv_win_cap = wcap;
       s->spmv_win_half = half;
-      if (s->opt_spmv_tile <= 0) tile = 512;   // one tile = one warp's strip of products
     }
+  }
+  // the ring kernels walk their own, shorter tiling: one tile = one warp's strip
+  int tile_ring = 0;
+  if (s->spmv_window) {
+    tile_ring = s->opt_spmv_tile > 0 ? s->opt_spmv_tile : (s->opt_spmv_variant == 4 ? 512 : 224);
+    if (tile_ring > 8192) tile_ring = 8192;
+    tile_ring = (tile_ring + 7) / 8 * 8;
   }
   if (tile > 8192) tile = 8192;   // 8192 complex entries + column ids = 164 KB of shared memory
   tile = (tile + 7) / 8 * 8;
@@ -697,6 +709,15 @@ int ab200_set_csr(ab200_solver* s, const void* indptr, int indptr_bits, const in
   REQUIRE(nblk < (1ll << 30), "too many SpMV tiles");
   CU(cudaMalloc(&s->rowblk, sizeof(int64_t) * 2 * (size_t)(nblk + 1)));
   CU(launch_spmv_plan(s->indptr, indptr_bits, s->n, nnz, tile, (int)nblk, s->rowblk, s->stream));
+  if (tile_ring > 0) {
+    int64_t nb2 = (nnz + tile_ring - 1) / tile_ring;
+    if (nb2 < 1) nb2 = 1;
+    REQUIRE(nb2 < (1ll << 30), "too many SpMV tiles");
+    CU(cudaMalloc(&s->rowblk_ring, sizeof(int64_t) * 2 * (size_t)(nb2 + 1)));
+    CU(launch_spmv_plan(s->indptr, indptr_bits, s->n, nnz, tile_ring, (int)nb2, s->rowblk_ring, s->stream));
+    s->tile_ring = tile_ring;
+    s->nblk_ring = (int)nb2;
+  }
   CU(cudaStreamSynchronize(s->stream));
   s->indptr_bits = indptr_bits;
   s->value_kind = value_kind;
@@ -903,11 +924,22 @@ static int enqueue_spmv(ab200_solver* s, const void* x, void* y, const double* x
   a.rp_cap = s->spmv_rp_cap;
   a.bps = s->opt_spmv_bps;
   a.nranks = s->nranks;
-  a.window = s->spmv_window && s->opt_spmv_variant == 0;
+  // ring kernels: float64 vectors only (complex128 vectors: half as many entries fit the ring and
+  // the tile kernel is faster); 2 = cp.async strips (default), 1 = register-staged (spmv_variant 4)
+  a.window = 0;
+  if (s->spmv_window && a.real && s->rowblk_ring != nullptr) {
+    if (s->opt_spmv_variant == 0 || s->opt_spmv_variant == 5) a.window = 2;
+    if (s->opt_spmv_variant == 4) a.window = 1;
+  }
+  if (a.window) {
+    a.rowblk = s->rowblk_ring;
+    a.nblocks = s->nblk_ring;
+    a.tile = s->tile_ring;
+  }
   a.contig = s->opt_spmv_variant == 3 ? 1 : 0;
   a.win_cap = s->spmv_win_cap;
   a.win_half = s->spmv_win_half;
-  a.ring_warps = s->opt_spmv_ring_warps > 0 ? s->opt_spmv_ring_warps : 15;
+  a.ring_warps = s->opt_spmv_ring_warps > 0 ? s->opt_spmv_ring_warps : (a.window == 2 ? 31 : 15);
   const double sv = s->value_kind == AB200_F64 ? 8.0 : 16.0;
   const double eb = a.real ? 8.0 : 16.0;
   const double bytes = (double)s->nnz * (sv + 4.0) + (double)s->n * (s->indptr_bits / 8 + 2.0 * eb) +

@@ -14,7 +14,9 @@
 //                       tile into a shared-memory ring with bulk copies (TMA) + mbarriers, one
 //                       consumer thread per row.  The default for such operators.
 //   spmv_stream_kernel  the same with cp.async staging and block barriers (round 1; A/B only).
-//   spmv_ring_kernel    skewed rows, float64 vectors: one warp per tile, x gathered from a
+//   spmv_ring2_kernel   skewed rows, float64 vectors: one warp per tile, strips staged with cp.async,
+//                       x gathered from a shared-memory ring that slides along the diagonal.
+//   spmv_ring_kernel    its predecessor (strips in registers, 15 warps; spmv_variant = 4): x gathered from a
 //                       shared-memory ring that slides along the diagonal.
 //   spmv_tile_kernel    everything else: one block per tile, x gathered from global memory, a
 //                       warp for segments > 16 entries, rows longer than a tile carried through y.
@@ -536,6 +538,70 @@ struct RingTile {
   int64_t r0, r1, k0, k1;   // rows and entries of a tile (r0 >= r1: nothing to do)
 };
 
+// The producer thread of the ring kernels: keeps the shared-memory ring of x up to kRingDepth
+// rounds ahead of the consumer warps (see spmv_ring_kernel).
+template <typename XT>
+__device__ __forceinline__ void ring_producer(const SpmvArgs& a, XT* ring, RingHdr* hdr,
+                                              unsigned long long* ring_full, unsigned long long* round_done,
+                                              int b0, int b1, int ncw, int rounds, int W, int nloc) {
+  constexpr int DM = kRingDepth - 1;
+  const int64_t* __restrict__ rowblk = a.rowblk;
+  const XT* __restrict__ x = static_cast<const XT*>(a.x);
+  constexpr int XA = 16 / (int)sizeof(XT);                 // x entries per 16 bytes
+  const int nloc_al = (nloc + XA - 1) & ~(XA - 1);          // columns are padded to 16 entries
+  const int H = a.win_half;
+  int cur_lo = 0, whi = 0;   // lower bound of the previous round's window; entries loaded so far
+  int hi_slot = 0, lo_slot = 0;   // ring slots of entries whi and cur_lo
+  for (int t = 0; t < rounds; ++t) {
+    // the consumer warps may be anywhere in rounds (t - depth, t): round t's copies may be
+    // issued once every warp has left round t - depth, and overwrite only slots below the
+    // lower bound of round t - depth + 1
+    if (t >= kRingDepth) mbar_wait(round_done + (t & DM), (unsigned)((t - kRingDepth) >> kRingDepthLog) & 1u);
+    const int bt = b0 + t * ncw;
+    const int bt1 = bt + ncw < b1 ? bt + ncw : b1;
+    const int64_t R0 = rowblk[bt], R1 = rowblk[bt1];
+    int64_t want_lo = R0 - H;
+    if (want_lo < 0) want_lo = 0;
+    if (want_lo > nloc_al) want_lo = nloc_al;
+    want_lo &= ~(int64_t)(XA - 1);
+    int64_t want_hi = R1 + H;
+    if (want_hi > nloc_al) want_hi = nloc_al;
+    want_hi = (want_hi + XA - 1) & ~(int64_t)(XA - 1);
+    int new_hi;
+    if (t == 0) {
+      whi = cur_lo = (int)want_lo;
+      hi_slot = lo_slot = 0;
+      new_hi = (int)(want_hi < want_lo + W ? want_hi : want_lo + W);
+    } else {
+      const int oldest = t - kRingDepth + 1 > 0 ? t - kRingDepth + 1 : 0;
+      const int64_t cap = (int64_t)hdr->lo[oldest & DM] + W;   // that round still reads from its lo on
+      const int64_t h = want_hi < cap ? want_hi : cap;
+      new_hi = h > whi ? (int)h : whi;
+    }
+    int next_lo = (int)want_lo;
+    if (next_lo < new_hi - W) next_lo = new_hi - W;
+    if (next_lo > new_hi) next_lo = new_hi;
+    if (next_lo < cur_lo) next_lo = cur_lo;
+    lo_slot += next_lo - cur_lo;   // < 2 W: one conditional subtraction
+    if (lo_slot >= W) lo_slot -= W;
+    hdr->lo[t & DM] = next_lo;
+    hdr->hi[t & DM] = new_hi;
+    hdr->slot[t & DM] = lo_slot;
+    const int cnt = new_hi - whi;   // multiple of XA, <= W
+    mbar_expect_tx(ring_full + (t & DM), (unsigned)cnt * (unsigned)sizeof(XT));  // release: hdr visible
+    if (cnt > 0) {
+      const int first = cnt < W - hi_slot ? cnt : W - hi_slot;
+      bulk_g2s(ring + hi_slot, x + whi, (unsigned)first * (unsigned)sizeof(XT), ring_full + (t & DM));
+      if (cnt > first)
+        bulk_g2s(ring, x + whi + first, (unsigned)(cnt - first) * (unsigned)sizeof(XT), ring_full + (t & DM));
+      hi_slot += cnt;
+      if (hi_slot >= W) hi_slot -= W;
+    }
+    whi = new_hi;
+    cur_lo = next_lo;
+  }
+}
+
 template <typename IdxT, typename ValT, typename XT, int MAXW>
 __global__ void __launch_bounds__((MAXW + 1) * 32, 1) spmv_ring_kernel(SpmvArgs a) {
   if (a.ctl != nullptr && a.ctl->stop) return;
@@ -575,61 +641,8 @@ __global__ void __launch_bounds__((MAXW + 1) * 32, 1) spmv_ring_kernel(SpmvArgs 
   const int warp = tid >> 5, lane = tid & 31;
 
   if (warp == ncw) {
-    // ---------------- producer (lane 0): keeps the ring one round ahead of the consumers
-    if (lane != 0) return;
-    constexpr int XA = 16 / (int)sizeof(XT);                 // x entries per 16 bytes
-    const int nloc_al = (nloc + XA - 1) & ~(XA - 1);          // columns are padded to 16 entries
-    const int H = a.win_half;
-    int cur_lo = 0, whi = 0;   // lower bound of the previous round's window; entries loaded so far
-    int hi_slot = 0, lo_slot = 0;   // ring slots of entries whi and cur_lo
-    for (int t = 0; t < rounds; ++t) {
-      // the consumer warps may be anywhere in rounds (t - depth, t): round t's copies may be
-      // issued once every warp has left round t - depth, and overwrite only slots below the
-      // lower bound of round t - depth + 1
-      if (t >= kRingDepth) mbar_wait(round_done + (t & DM), (unsigned)((t - kRingDepth) >> kRingDepthLog) & 1u);
-      const int bt = b0 + t * ncw;
-      const int bt1 = bt + ncw < b1 ? bt + ncw : b1;
-      const int64_t R0 = rowblk[bt], R1 = rowblk[bt1];
-      int64_t want_lo = R0 - H;
-      if (want_lo < 0) want_lo = 0;
-      if (want_lo > nloc_al) want_lo = nloc_al;
-      want_lo &= ~(int64_t)(XA - 1);
-      int64_t want_hi = R1 + H;
-      if (want_hi > nloc_al) want_hi = nloc_al;
-      want_hi = (want_hi + XA - 1) & ~(int64_t)(XA - 1);
-      int new_hi;
-      if (t == 0) {
-        whi = cur_lo = (int)want_lo;
-        hi_slot = lo_slot = 0;
-        new_hi = (int)(want_hi < want_lo + W ? want_hi : want_lo + W);
-      } else {
-        const int oldest = t - kRingDepth + 1 > 0 ? t - kRingDepth + 1 : 0;
-        const int64_t cap = (int64_t)hdr->lo[oldest & DM] + W;   // that round still reads from its lo on
-        const int64_t h = want_hi < cap ? want_hi : cap;
-        new_hi = h > whi ? (int)h : whi;
-      }
-      int next_lo = (int)want_lo;
-      if (next_lo < new_hi - W) next_lo = new_hi - W;
-      if (next_lo > new_hi) next_lo = new_hi;
-      if (next_lo < cur_lo) next_lo = cur_lo;
-      lo_slot += next_lo - cur_lo;   // < 2 W: one conditional subtraction
-      if (lo_slot >= W) lo_slot -= W;
-      hdr->lo[t & DM] = next_lo;
-      hdr->hi[t & DM] = new_hi;
-      hdr->slot[t & DM] = lo_slot;
-      const int cnt = new_hi - whi;   // multiple of XA, <= W
-      mbar_expect_tx(ring_full + (t & DM), (unsigned)cnt * (unsigned)sizeof(XT));  // release: hdr visible
-      if (cnt > 0) {
-        const int first = cnt < W - hi_slot ? cnt : W - hi_slot;
-        bulk_g2s(ring + hi_slot, x + whi, (unsigned)first * (unsigned)sizeof(XT), ring_full + (t & DM));
-        if (cnt > first)
-          bulk_g2s(ring, x + whi + first, (unsigned)(cnt - first) * (unsigned)sizeof(XT), ring_full + (t & DM));
-        hi_slot += cnt;
-        if (hi_slot >= W) hi_slot -= W;
-      }
-      whi = new_hi;
-      cur_lo = next_lo;
-    }
+    // ---------------- producer (lane 0): keeps the ring ahead of the consumers
+    if (lane == 0) ring_producer<XT>(a, ring, hdr, ring_full, round_done, b0, b1, ncw, rounds, W, nloc);
     return;
   }
 
@@ -840,6 +853,244 @@ __global__ void __launch_bounds__((MAXW + 1) * 32, 1) spmv_ring_kernel(SpmvArgs 
   }
 }
 
+// ------------------------------------------------------------------ ring kernel, strips staged with cp.async
+// Same decomposition and arithmetic as spmv_ring_kernel (float64 values and vectors); what
+// differs is where a strip of the CSR stream waits.  There the 4 column ids + 4 values per lane
+// and 128-entry group sit in REGISTERS while in flight (60 of the 128 registers a thread may
+// use with 16 warps per SM), and ncu shows the kernel latency-bound at 4 warps per scheduler with
+// every unit under 40 % (profiles/r02_spmv_ring.md).  Here a warp stages its strip into its own
+// shared-memory buffer with cp.async (LDGSTS: no register holds data in flight), forms the
+// products in place (a product overwrites its value) and sums the rows from there; a thread
+// needs < 64 registers, so up to 31 consumer warps + the producer fit one SM.  The strip is
+// shorter (kRing2Strip entries: the buffers share the SM with the ring) and a warp's next strip
+// is requested only when its rows are summed -- the other 30 warps cover that round trip.
+constexpr int kRing2Iters = 3;
+constexpr int kRing2Strip = 128 * kRing2Iters;   // 384 entries: 4.5 KB per warp
+constexpr int kRing2RowGroups = 3;
+
+__device__ __forceinline__ void cpa16_hint(void* dst, const void* src, unsigned long long pol) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "l"(pol)
+               : "memory");
+}
+
+template <typename IdxT>
+__global__ void __launch_bounds__(1024, 1) spmv_ring2_kernel(SpmvArgs a) {
+  if (a.ctl != nullptr && a.ctl->stop) return;
+  extern __shared__ __align__(128) unsigned char ring_smem[];
+  const int ncw = (int)(blockDim.x >> 5) - 1;   // consumer warps; the last warp is the producer
+  const int W = a.win_cap;
+  double* ring = reinterpret_cast<double*>(ring_smem);
+  unsigned char* strips = reinterpret_cast<unsigned char*>(ring + W);
+  constexpr size_t kStripBytes = (size_t)kRing2Strip * 12;   // values (8 B) then column ids (4 B)
+  unsigned char* tail = strips + (size_t)ncw * kStripBytes;
+  RingHdr* hdr = reinterpret_cast<RingHdr*>(tail);
+  unsigned long long* ring_full = reinterpret_cast<unsigned long long*>(tail + sizeof(RingHdr));  // [depth]
+  unsigned long long* round_done = ring_full + kRingDepth;                                         // [depth]
+  constexpr int DM = kRingDepth - 1;
+
+  const int per = (a.nblocks + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int b0 = (int)blockIdx.x * per;
+  const int b1 = b0 + per < a.nblocks ? b0 + per : a.nblocks;
+  if (b0 >= b1) return;
+  const int rounds = (b1 - b0 + ncw - 1) / ncw;
+
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int i = 0; i < kRingDepth; ++i) {
+      mbar_init(ring_full + i, 1);
+      mbar_init(round_done + i, ncw);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int64_t* __restrict__ rowblk = a.rowblk;
+  const int64_t* __restrict__ nnzblk = a.rowblk + a.nblocks + 1;
+  const double* __restrict__ x = static_cast<const double*>(a.x);
+  const int nloc = a.n_local_cols > 0x7fffffff ? 0x7fffffff : (int)a.n_local_cols;
+  const int warp = tid >> 5, lane = tid & 31;
+
+  if (warp == ncw) {
+    if (lane == 0) ring_producer<double>(a, ring, hdr, ring_full, round_done, b0, b1, ncw, rounds, W, nloc);
+    return;
+  }
+
+  // ---------------- consumer warps
+  const IdxT* __restrict__ indptr = static_cast<const IdxT*>(a.indptr);
+  const double* __restrict__ values = static_cast<const double*>(a.values);
+  const int32_t* __restrict__ indices = a.indices;
+  const double* __restrict__ ghost = static_cast<const double*>(a.ghost);
+  double* __restrict__ yout = static_cast<double*>(a.y);
+  double* sval = reinterpret_cast<double*>(strips + (size_t)warp * kStripBytes);   // values, then products
+  int32_t* scol = reinterpret_cast<int32_t*>(sval + kRing2Strip);
+  const double xs = a.xscale ? *a.xscale : 1.0;
+  const unsigned long long l2pol = l2_policy_evict_first();
+
+  auto load_tile = [&](int tt) {
+    RingTile T = {0, 0, 0, 0};
+    const int b = b0 + tt * ncw + warp;
+    if (tt < rounds && b < b1) {
+      T.r0 = rowblk[b], T.r1 = rowblk[b + 1];
+      T.k0 = nnzblk[b], T.k1 = nnzblk[b + 1];
+    }
+    return T;
+  };
+  // request the strip that starts at the 4-aligned entry ca (cp.async, 16 bytes per request)
+  auto request = [&](int64_t ca, int64_t k1) {
+    const int tot = (int)((ca + kRing2Strip < k1 ? ca + kRing2Strip : k1) - ca);
+    const int ngrp = (tot + 3) >> 2;   // groups of 4 entries; the arrays carry 8 spare entries
+    for (int g = lane; g < ngrp; g += kWarp) {
+      cpa16_hint(scol + 4 * g, indices + ca + 4 * g, l2pol);
+      cpa16_hint(sval + 4 * g, values + ca + 4 * g, l2pol);
+      cpa16_hint(sval + 4 * g + 2, values + ca + 4 * g + 2, l2pol);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  IdxT rp[kRing2RowGroups];
+  auto request_rowptr = [&](const RingTile& T) {
+#pragma unroll
+    for (int q = 0; q < kRing2RowGroups; ++q) {
+      int64_t row = T.r0 + q * kWarp + lane;
+      if (row > T.r1) row = T.r1;
+      rp[q] = indptr[row];
+    }
+  };
+
+  int t = 0;
+  RingTile cur = load_tile(0), nxt = load_tile(1);
+  auto skip_idle = [&]() {
+    while (t < rounds && cur.r0 >= cur.r1) {
+      mbar_wait(ring_full + (t & DM), (unsigned)(t >> kRingDepthLog) & 1u);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(round_done + (t & DM));
+      ++t;
+      cur = nxt;
+      nxt = load_tile(t + 1);
+    }
+  };
+  skip_idle();
+  int64_t ca = cur.k0 & ~(int64_t)3, cs = cur.k0;
+  if (t < rounds) {
+    request(ca, cur.k1);
+    request_rowptr(cur);
+  }
+  int wlo = 0, wslot = 0;
+  unsigned wlen = 0;
+  while (t < rounds) {
+    const int64_t ce = ca + kRing2Strip < cur.k1 ? ca + kRing2Strip : cur.k1;
+    const int tot = (int)(ce - ca);
+    const bool first = (cs == cur.k0);
+    if (first) {
+      mbar_wait(ring_full + (t & DM), (unsigned)(t >> kRingDepthLog) & 1u);
+      wlo = hdr->lo[t & DM];
+      wslot = hdr->slot[t & DM];
+      int whi = hdr->hi[t & DM];
+      if (whi > nloc) whi = nloc;
+      wlen = whi > wlo ? (unsigned)(whi - wlo) : 0u;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    // ---- products in place, lanes along the entries (x from the ring; every entry also issues
+    //      one global gather, at a dummy address when the ring has it -- see spmv_ring_kernel)
+#pragma unroll
+    for (int it = 0; it < kRing2Iters; ++it) {
+      const int g = it * kWarp + lane;
+      if (4 * g < tot) {
+        const int4 c4 = *reinterpret_cast<const int4*>(scol + 4 * g);
+        const double2 va = *reinterpret_cast<const double2*>(sval + 4 * g);
+        const double2 vb = *reinterpret_cast<const double2*>(sval + 4 * g + 2);
+        const int col[4] = {c4.x, c4.y, c4.z, c4.w};
+        const double av[4] = {va.x, va.y, vb.x, vb.y};
+        double xg[4];
+        unsigned off[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          off[u] = (unsigned)(col[u] - wlo);
+          const double* src = (col[u] < nloc) ? x + col[u] : ghost + (col[u] - nloc);
+          xg[u] = ld_ro(off[u] < wlen ? x : src);
+        }
+        double pr[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          double xv = xg[u];
+          if (off[u] < wlen) {
+            int sl = (int)off[u] + wslot;
+            if (sl >= W) sl -= W;
+            xv = ring[sl];
+          }
+          pr[u] = vmul(av[u], xv);
+        }
+        *reinterpret_cast<double2*>(sval + 4 * g) = make_double2(pr[0], pr[1]);
+        *reinterpret_cast<double2*>(sval + 4 * g + 2) = make_double2(pr[2], pr[3]);
+      }
+    }
+    __syncwarp();
+    // ---- rows, lanes along the rows, stored order
+    const double* prod = sval;
+    int grp = 0;
+    for (int64_t rb = cur.r0; rb < cur.r1; rb += kWarp, ++grp) {
+      const int64_t row = rb + lane;
+      const bool act = row < cur.r1;
+      int64_t rs, re;
+      if (grp < kRing2RowGroups - 1) {
+        IdxT mine = rp[0], next0 = rp[1];
+#pragma unroll
+        for (int q = 1; q < kRing2RowGroups - 1; ++q)
+          if (grp == q) mine = rp[q], next0 = rp[q + 1];
+        IdxT up = __shfl_down_sync(0xffffffffu, mine, 1);
+        const IdxT wrap = __shfl_sync(0xffffffffu, next0, 0);
+        if (lane == kWarp - 1) up = wrap;
+        rs = act ? (int64_t)mine : 0;
+        re = act ? (int64_t)up : 0;
+      } else {
+        rs = act ? (int64_t)indptr[row] : 0;
+        re = act ? (int64_t)indptr[row + 1] : 0;
+      }
+      const int64_t lo = rs > cs ? rs : cs;
+      const int64_t hi = re < ce ? re : ce;
+      const bool has = act && (hi > lo || (rs == re && first));
+      const int kb = (int)(lo - ca), ke = (int)(hi - ca);
+      const bool lng = has && (ke - kb > kRingLongSeg);
+      double acc = 0.0;
+      if (has && rs < cs) acc = yout[row];
+      if (has && !lng)
+        for (int k = kb; k < ke; ++k) acc = cadd_rn(acc, prod[k]);
+      unsigned m = __ballot_sync(0xffffffffu, lng);
+      while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        const int sb = __shfl_sync(0xffffffffu, kb, src);
+        const int se = __shfl_sync(0xffffffffu, ke, src);
+        double part = 0.0;
+        for (int k = sb + lane; k < se; k += kWarp) part = cadd_rn(part, prod[k]);
+        part = warp_sum(part);
+        if (lane == src) acc = cadd_rn(acc, part);
+      }
+      if (has) yout[row] = (re <= ce) ? cscale(acc, xs) : acc;
+    }
+    __syncwarp();   // the strip buffer may be refilled
+    if (ca + kRing2Strip < cur.k1) {
+      ca += kRing2Strip;
+      cs = ca;
+      request(ca, cur.k1);
+    } else {
+      if (lane == 0) mbar_arrive(round_done + (t & DM));
+      ++t;
+      cur = nxt;
+      nxt = load_tile(t + 1);
+      skip_idle();
+      ca = cur.k0 & ~(int64_t)3;
+      cs = cur.k0;
+      if (t < rounds) {
+        request(ca, cur.k1);
+        request_rowptr(cur);
+      }
+    }
+  }
+}
+
 cudaError_t launch_spmv_maxrow(const void* indptr, int indptr_bits, int64_t n, int* out,
                                cudaStream_t st) {
   int64_t grid = (n + 255) / 256;
@@ -1022,11 +1273,44 @@ static cudaError_t launch_spmv_ring(const SpmvArgs& a, cudaStream_t st) {
   return cudaGetLastError();
 }
 
+size_t spmv_ring2_smem(int win_cap, int nwarps) {
+  return (size_t)win_cap * 8 + (size_t)nwarps * kRing2Strip * 12 + sizeof(RingHdr) +
+         2 * kRingDepth * sizeof(unsigned long long);
+}
+
+template <typename IdxT>
+static cudaError_t launch_spmv_ring2(const SpmvArgs& a, cudaStream_t st) {
+  int nwarps = a.ring_warps;
+  if (nwarps > 31) nwarps = 31;
+  if (nwarps < 1) nwarps = 1;
+  int wcap = a.win_cap;
+  const int fit = (int)((227 * 1024 - spmv_ring2_smem(0, nwarps)) / 8) / 256 * 256;
+  if (wcap > fit) wcap = fit;
+  wcap = wcap / 16 * 16;
+  if (wcap < 256) wcap = 256;
+  SpmvArgs b = a;
+  b.win_cap = wcap;
+  if (b.win_half > (wcap - 1536) / 2) b.win_half = (wcap - 1536) / 2;
+  if (b.win_half < 0) b.win_half = 0;
+  const size_t smem = spmv_ring2_smem(wcap, nwarps);
+  static PerDeviceOnce once;
+  if (once.first_use()) {
+    cudaFuncSetAttribute(spmv_ring2_kernel<IdxT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  }
+  int64_t grid = a.num_sms;
+  const int64_t need = (a.nblocks + nwarps - 1) / nwarps;
+  if (grid > need) grid = need;
+  if (grid < 1) grid = 1;
+  spmv_ring2_kernel<IdxT><<<(int)grid, (nwarps + 1) * kWarp, smem, st>>>(b);
+  return cudaGetLastError();
+}
+
 template <typename IdxT, typename ValT, typename XT, int THREADS>
 static cudaError_t launch_spmv_tt(const SpmvArgs& a, cudaStream_t st) {
   // the ring kernel serves float64 vectors (real storage); with complex128 vectors half as many
   // entries fit the ring and the strips, and the tile kernel is faster (1.33 vs 2.0 ms, n = 1e7)
   if constexpr (sizeof(XT) == 8) {
+    if (a.window == 2) return launch_spmv_ring2<IdxT>(a, st);
     if (a.window) return launch_spmv_ring<IdxT, ValT, XT>(a, st);
   }
   if (!a.long_rows && a.variant == 0) return launch_spmv_bulk<IdxT, ValT, XT>(a, st);

@@ -451,10 +451,14 @@ def _local_skewed(n, rng, long_rows=()):
 @pytest.mark.parametrize("opts", [dict(), dict(spmv_tile=1024), dict(spmv_window=2048),
                                   dict(spmv_tile=8192, spmv_bps=2),
                                   dict(spmv_window=1024, spmv_ring_warps=3, spmv_tile=256),
-                                  dict(spmv_win_half=100), dict(spmv_tile=640, spmv_ring_warps=1)])
+                                  dict(spmv_win_half=100), dict(spmv_tile=640, spmv_ring_warps=1),
+                                  dict(spmv_tile=256, spmv_ring_warps=7, spmv_window=2048),
+                                  dict(spmv_variant=4), dict(spmv_variant=4, spmv_tile=1024),
+                                  dict(spmv_variant=4, spmv_window=1024, spmv_ring_warps=3, spmv_tile=256)])
 def test_spmv_window_kernel(gpu, opts):
     """Skewed rows with local columns (AB200_SPMV_MERGE / AUTO): x gathered from a sliding ring
-    in shared memory (spmv_ring_kernel), every ring / tile / warp shape.  Rows of <= 16 entries
+    in shared memory -- spmv_ring2_kernel (cp.async strips, the default) and spmv_ring_kernel
+    (register-staged, spmv_variant=4) -- every ring / tile / warp shape.  Rows of <= 16 entries
     stay bit-identical to scipy; longer ones within 1e-13 of the row's absolute sum.  Real and
     complex vectors, complex values, rows longer than several tiles, runs of empty rows."""
     from arnoldi_b200.matrices import powerlaw

@@ -1,5 +1,5 @@
 cd /root/repo
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_round2.py -x -q -m gpu -k "ortho or fused or arnoldi" > gpurun_out/r6_t_ortho.log 2>&1; tail -2 gpurun_out/r6_t_ortho.log
-timeout 300 python tools/sweep.py --grid 4096 --cycles 4 "" "ortho_variant=2" "ortho_variant=3" > gpurun_out/r6_sweep_fused.log 2>&1; cat gpurun_out/r6_sweep_fused.log
-timeout 300 python tools/sweep.py --grid 4096 --cycles 3 --complex-storage "" > gpurun_out/r6_sweep_fused_c.log 2>&1; cat gpurun_out/r6_sweep_fused_c.log
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
+timeout 600 $TR --master-port 29517 tests/mgpu_worker.py > gpurun_out/r6_mgpu2.log 2>&1; echo "rc=$?" >> gpurun_out/r6_mgpu2.log; grep "mgpu\]" gpurun_out/r6_mgpu2.log | tail -6; tail -2 gpurun_out/r6_mgpu2.log
+timeout 300 $TR --master-port 29518 tools/solve_dist.py --matrix powerlaw --rows 4000000 --top-base 2 --top-step 0.01 --real-arith pairs --fast-real-schur > gpurun_out/r6_pl2.json 2> gpurun_out/r6_pl2.err; cut -c 1-900 gpurun_out/r6_pl2.json | tail -2
