@@ -474,11 +474,14 @@ def test_spmv_window_kernel(gpu, opts):
         lens = np.diff(A.indptr)
         short = lens <= 16
         Aabs = abs(A.copy())
-        for algo in ("merge", "auto"):
+        for algo in ("merge", "auto", "merge64"):
             with DeviceSolver(n, 2) as dev:
                 for k, v in opts.items():
                     dev.set_option(k, v)
-                dev.set_csr(A.indptr, A.indices, A.data, algo=algo)
+                if algo == "merge64":       # 64-bit row pointers: the other instantiation
+                    dev.set_csr(A.indptr.astype(np.int64), A.indices, A.data, algo="merge")
+                else:
+                    dev.set_csr(A.indptr, A.indices, A.data, algo=algo)
                 for x in (rng.standard_normal(n) + 1j * rng.standard_normal(n),
                           rng.standard_normal(n).astype(np.complex128)):
                     y = dev.spmv(x)
