@@ -183,6 +183,11 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// the same for waits that can last microseconds (a whole round of another warp): sleep between
+// polls so the spinning warp does not take issue slots from the working ones
+__device__ __forceinline__ void mbar_wait_backoff(unsigned long long* bar, unsigned parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(64);
+}
 // global -> shared bulk copy; dst, src and bytes are multiples of 16
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes,
                                          unsigned long long* bar) {

@@ -527,8 +527,13 @@ constexpr int kRingStrip = 128 * kRingIters;    // products a warp parks per str
 constexpr int kRingLongSeg = 32;                // segments longer than this are summed by the warp
 constexpr int kRingRowGroups = 5;               // groups of 32 row pointers fetched ahead per tile
 
-constexpr int kRingDepthLog = 3;
-constexpr int kRingDepth = 1 << kRingDepthLog;   // rounds the consumer warps may drift apart
+constexpr int kRingDepthLog = 4;
+constexpr int kRingDepth = 1 << kRingDepthLog;   // capacity of the hand-shake arrays
+// rounds the consumer warps may drift apart, per kernel (measured, power-law n = 1e7): the
+// register-staged kernel 0.92 ms at 8 and 0.88 ms at 16; the cp.async kernel 0.73 ms at 8 and
+// 1.14 ms at 16 (its rounds are shorter: a deep drift truncates the leading rounds' windows)
+constexpr int kRing1DepthLog = 4;
+constexpr int kRing2DepthLog = 3;
 struct RingHdr {
   int lo[kRingDepth], hi[kRingDepth];   // x entries [lo, hi) valid in the ring for round t (slot t % depth)
   int slot[kRingDepth];                 // ring slot of entry lo
@@ -540,11 +545,12 @@ struct RingTile {
 
 // The producer thread of the ring kernels: keeps the shared-memory ring of x up to kRingDepth
 // rounds ahead of the consumer warps (see spmv_ring_kernel).
-template <typename XT>
+template <typename XT, int DLOG>
 __device__ __forceinline__ void ring_producer(const SpmvArgs& a, XT* ring, RingHdr* hdr,
                                               unsigned long long* ring_full, unsigned long long* round_done,
                                               int b0, int b1, int ncw, int rounds, int W, int nloc) {
-  constexpr int DM = kRingDepth - 1;
+  constexpr int DEPTH = 1 << DLOG;
+  constexpr int DM = DEPTH - 1;
   const int64_t* __restrict__ rowblk = a.rowblk;
   const XT* __restrict__ x = static_cast<const XT*>(a.x);
   constexpr int XA = 16 / (int)sizeof(XT);                 // x entries per 16 bytes
@@ -556,7 +562,7 @@ __device__ __forceinline__ void ring_producer(const SpmvArgs& a, XT* ring, RingH
     // the consumer warps may be anywhere in rounds (t - depth, t): round t's copies may be
     // issued once every warp has left round t - depth, and overwrite only slots below the
     // lower bound of round t - depth + 1
-    if (t >= kRingDepth) mbar_wait(round_done + (t & DM), (unsigned)((t - kRingDepth) >> kRingDepthLog) & 1u);
+    if (t >= DEPTH) mbar_wait(round_done + (t & DM), (unsigned)((t - DEPTH) >> DLOG) & 1u);
     const int bt = b0 + t * ncw;
     const int bt1 = bt + ncw < b1 ? bt + ncw : b1;
     const int64_t R0 = rowblk[bt], R1 = rowblk[bt1];
@@ -573,7 +579,7 @@ __device__ __forceinline__ void ring_producer(const SpmvArgs& a, XT* ring, RingH
       hi_slot = lo_slot = 0;
       new_hi = (int)(want_hi < want_lo + W ? want_hi : want_lo + W);
     } else {
-      const int oldest = t - kRingDepth + 1 > 0 ? t - kRingDepth + 1 : 0;
+      const int oldest = t - DEPTH + 1 > 0 ? t - DEPTH + 1 : 0;
       const int64_t cap = (int64_t)hdr->lo[oldest & DM] + W;   // that round still reads from its lo on
       const int64_t h = want_hi < cap ? want_hi : cap;
       new_hi = h > whi ? (int)h : whi;
@@ -614,7 +620,8 @@ __global__ void __launch_bounds__((MAXW + 1) * 32, 1) spmv_ring_kernel(SpmvArgs 
   RingHdr* hdr = reinterpret_cast<RingHdr*>(tail);
   unsigned long long* ring_full = reinterpret_cast<unsigned long long*>(tail + sizeof(RingHdr));  // [depth]
   unsigned long long* round_done = ring_full + kRingDepth;                                         // [depth]
-  constexpr int DM = kRingDepth - 1;
+  constexpr int DLOG = kRing1DepthLog;
+  constexpr int DM = (1 << DLOG) - 1;
 
   // contiguous share of the tiles for this block
   const int per = (a.nblocks + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -625,7 +632,7 @@ __global__ void __launch_bounds__((MAXW + 1) * 32, 1) spmv_ring_kernel(SpmvArgs 
 
   const int tid = threadIdx.x;
   if (tid == 0) {
-    for (int i = 0; i < kRingDepth; ++i) {
+    for (int i = 0; i <= DM; ++i) {
       mbar_init(ring_full + i, 1);
       mbar_init(round_done + i, ncw);
     }
@@ -642,7 +649,7 @@ __global__ void __launch_bounds__((MAXW + 1) * 32, 1) spmv_ring_kernel(SpmvArgs 
 
   if (warp == ncw) {
     // ---------------- producer (lane 0): keeps the ring ahead of the consumers
-    if (lane == 0) ring_producer<XT>(a, ring, hdr, ring_full, round_done, b0, b1, ncw, rounds, W, nloc);
+    if (lane == 0) ring_producer<XT, DLOG>(a, ring, hdr, ring_full, round_done, b0, b1, ncw, rounds, W, nloc);
     return;
   }
 
@@ -698,7 +705,7 @@ __global__ void __launch_bounds__((MAXW + 1) * 32, 1) spmv_ring_kernel(SpmvArgs 
   // rounds in which this warp has no rows still take part in the hand-shake, in order
   auto skip_idle = [&]() {
     while (t < rounds && cur.r0 >= cur.r1) {
-      mbar_wait(ring_full + (t & DM), (unsigned)(t >> kRingDepthLog) & 1u);
+      mbar_wait(ring_full + (t & DM), (unsigned)(t >> DLOG) & 1u);
       __syncwarp();
       if (lane == 0) mbar_arrive(round_done + (t & DM));
       ++t;
@@ -721,7 +728,7 @@ __global__ void __launch_bounds__((MAXW + 1) * 32, 1) spmv_ring_kernel(SpmvArgs 
     const int tot = (int)(ce - ca);
     const bool first = (cs == cur.k0);
     if (first) {
-      mbar_wait(ring_full + (t & DM), (unsigned)(t >> kRingDepthLog) & 1u);
+      mbar_wait(ring_full + (t & DM), (unsigned)(t >> DLOG) & 1u);
       wlo = hdr->lo[t & DM];
       wslot = hdr->slot[t & DM];
       int whi = hdr->hi[t & DM];
@@ -887,7 +894,8 @@ __global__ void __launch_bounds__(1024, 1) spmv_ring2_kernel(SpmvArgs a) {
   RingHdr* hdr = reinterpret_cast<RingHdr*>(tail);
   unsigned long long* ring_full = reinterpret_cast<unsigned long long*>(tail + sizeof(RingHdr));  // [depth]
   unsigned long long* round_done = ring_full + kRingDepth;                                         // [depth]
-  constexpr int DM = kRingDepth - 1;
+  constexpr int DLOG = kRing2DepthLog;
+  constexpr int DM = (1 << DLOG) - 1;
 
   const int per = (a.nblocks + (int)gridDim.x - 1) / (int)gridDim.x;
   const int b0 = (int)blockIdx.x * per;
@@ -897,7 +905,7 @@ __global__ void __launch_bounds__(1024, 1) spmv_ring2_kernel(SpmvArgs a) {
 
   const int tid = threadIdx.x;
   if (tid == 0) {
-    for (int i = 0; i < kRingDepth; ++i) {
+    for (int i = 0; i <= DM; ++i) {
       mbar_init(ring_full + i, 1);
       mbar_init(round_done + i, ncw);
     }
@@ -913,7 +921,7 @@ __global__ void __launch_bounds__(1024, 1) spmv_ring2_kernel(SpmvArgs a) {
   const int warp = tid >> 5, lane = tid & 31;
 
   if (warp == ncw) {
-    if (lane == 0) ring_producer<double>(a, ring, hdr, ring_full, round_done, b0, b1, ncw, rounds, W, nloc);
+    if (lane == 0) ring_producer<double, DLOG>(a, ring, hdr, ring_full, round_done, b0, b1, ncw, rounds, W, nloc);
     return;
   }
 
@@ -962,7 +970,7 @@ __global__ void __launch_bounds__(1024, 1) spmv_ring2_kernel(SpmvArgs a) {
   RingTile cur = load_tile(0), nxt = load_tile(1);
   auto skip_idle = [&]() {
     while (t < rounds && cur.r0 >= cur.r1) {
-      mbar_wait(ring_full + (t & DM), (unsigned)(t >> kRingDepthLog) & 1u);
+      mbar_wait(ring_full + (t & DM), (unsigned)(t >> DLOG) & 1u);
       __syncwarp();
       if (lane == 0) mbar_arrive(round_done + (t & DM));
       ++t;
@@ -983,7 +991,7 @@ __global__ void __launch_bounds__(1024, 1) spmv_ring2_kernel(SpmvArgs a) {
     const int tot = (int)(ce - ca);
     const bool first = (cs == cur.k0);
     if (first) {
-      mbar_wait(ring_full + (t & DM), (unsigned)(t >> kRingDepthLog) & 1u);
+      mbar_wait(ring_full + (t & DM), (unsigned)(t >> DLOG) & 1u);
       wlo = hdr->lo[t & DM];
       wslot = hdr->slot[t & DM];
       int whi = hdr->hi[t & DM];
